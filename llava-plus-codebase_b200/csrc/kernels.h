@@ -1,0 +1,106 @@
+// Internal launcher declarations for the b2llava kernels (C++ side, not part of the C ABI).
+// All tensors are device pointers; activations/weights are bf16 unless stated otherwise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2 {
+
+enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_SWIGLU = 3 };
+enum { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
+
+int num_sms();
+
+// ---- tcgen05 GEMM (gemm_tcgen05.cu) -------------------------------------------------------------
+// out[M, N] = act(A[M,K] · W[N,K]^T + bias) + residual      (ACT_NONE / QUICK_GELU / GELU_ERF)
+// out[M, N/2] = silu(gate) * up                               (ACT_SWIGLU; W rows block-64 interleaved)
+struct GemmArgs {
+    const void* A = nullptr; int lda = 0;        // bf16 [M, K]
+    const void* W = nullptr; int ldw = 0;        // bf16 [N, K]
+    const void* bias = nullptr;                  // bf16 [N] or null
+    const void* residual = nullptr; int ld_res = 0;  // bf16 [M, N] or null (may alias out)
+    void* out = nullptr; int ld_out = 0; int out_fp32 = 0;
+    int M = 0, N = 0, K = 0;
+    int act = ACT_NONE;
+    int bn_override = 0;  // 0 = heuristic, else 64/128/256
+};
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+
+// ---- weight-streaming GEMV for decode (gemv.cu) ---------------------------------------------------
+// out[B, N] = (rmsnorm(x) or x)[B,K] · W[N,K]^T (+ residual); B <= 8. ACT_SWIGLU: out[B, N/2].
+struct GemvArgs {
+    const void* x = nullptr; int64_t ldx = 0;   // bf16 [B, K], row stride ldx (elements)
+    const void* W = nullptr; int ldw = 0;        // bf16 [N, K]
+    const void* norm_gamma = nullptr; float eps = 0.f;  // fused RMSNorm on x when non-null
+    const void* residual = nullptr; int ld_res = 0;     // bf16 [B, N] or null (may alias out)
+    void* out = nullptr; int ld_out = 0; int out_fp32 = 0;
+    int B = 0, N = 0, K = 0;
+    int act = ACT_NONE;
+};
+int gemv_bf16(const GemvArgs& g, cudaStream_t stream);
+
+// ---- norms (norms.cu) ------------------------------------------------------------------------------
+int layernorm_bf16(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,
+                   cudaStream_t stream);
+// HF LlamaRMSNorm semantics: y = gamma * bf16(x * rsqrt(mean(x^2) + eps)); x rows may be strided.
+int rmsnorm_bf16(const void* x, int64_t x_row_stride, const void* gamma, void* y, int rows, int cols, float eps,
+                 cudaStream_t stream);
+// gather variant: row r of y is the RMSNorm of x[row_index[r]] (row_index on device)
+int rmsnorm_gather_bf16(const void* x, const int32_t* row_index, const void* gamma, void* y, int rows, int cols,
+                        float eps, cudaStream_t stream);
+
+// ---- ViT helpers (vit_ops.cu) ----------------------------------------------------------------------
+// pixels [B,3,img,img] bf16 -> patches [B*P, kpad] (k = c*patch*patch + i*patch + j, zero padded to kpad)
+int vit_im2col(const void* pixels, void* out, int B, int img, int patch, int kpad, cudaStream_t stream);
+// hidden[b, 0] = LN(cls + pos[0]); hidden[b, 1+p] = LN(patch_out[b*P+p] + pos[1+p])   (pre_layrnorm fused)
+int vit_embed_ln(const void* patch_out, const void* cls, const void* pos, const void* gamma, const void* beta,
+                 void* hidden, int B, int P, int D, float eps, cudaStream_t stream);
+// out[b, p, :] = hidden[b, 1 + p, :]   (feature_select 'patch': drop CLS)
+int vit_drop_cls(const void* hidden, void* out, int B, int P, int D, cudaStream_t stream);
+
+// ---- attention (attention.cu) ----------------------------------------------------------------------
+struct FlashArgs {
+    const void* q = nullptr; int64_t q_bs = 0, q_ts = 0, q_hs = 0;  // element strides: batch, token, head
+    const void* k = nullptr; int64_t k_bs = 0, k_ts = 0, k_hs = 0;
+    const void* v = nullptr; int64_t v_bs = 0, v_ts = 0, v_hs = 0;
+    void* o = nullptr;       int64_t o_bs = 0, o_ts = 0, o_hs = 0;
+    const int32_t* seq_lens = nullptr;  // device [B] or null (=S)
+    int B = 0, H = 0, S = 0, D = 0;     // S = padded/query length; D in {64, 128}
+    int causal = 0;
+    float scale = 1.f;
+};
+int flash_attn_bf16(const FlashArgs& a, cudaStream_t stream);
+
+// prefill: RoPE on q (in place) and k inside qkv [B*S, 3*H*D]; roped k and v written to the cache
+// kcache/vcache: [Bmax, H, Smax, D] for one layer. Positions are 0..S-1 (right-padded rows).
+int rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, int D, int Smax, float theta,
+                  cudaStream_t stream);
+
+// decode: q/k/v of the new token from qkv [B, 3*H*D]; RoPE at position cur_len[b]; append k,v to the cache;
+// split-KV attention over cur_len[b]+1 keys; out [B, H*D] bf16.
+struct DecodeAttnArgs {
+    const void* qkv = nullptr;
+    void* kcache = nullptr; void* vcache = nullptr;  // layer base, [Bmax, H, Smax, D]
+    const int32_t* cur_len = nullptr;                // device [B]
+    void* out = nullptr;
+    float* partial = nullptr;                        // workspace [B*H*nsplit*(D+2)] fp32
+    int32_t* counters = nullptr;                     // workspace [B*H], zero-initialised, self-resetting
+    int B = 0, H = 0, D = 128, Smax = 0, nsplit = 1;
+    float theta = 10000.f, scale = 1.f;
+};
+int decode_attn_bf16(const DecodeAttnArgs& a, cudaStream_t stream);
+
+// ---- misc (misc_ops.cu) ----------------------------------------------------------------------------
+// out[r, :] = src_index[r] >= 0 ? table[src_index[r]] : (src_index[r] == INT32_MIN ? 0 : feats[-src_index[r]-1])
+int splice_embed(const int32_t* src_index, const void* table, const void* feats, void* out, int rows, int h,
+                 cudaStream_t stream);
+int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab,
+                 cudaStream_t stream);
+int argmax_f32(const float* logits, int B, int V, int32_t* out, cudaStream_t stream);
+int add_i32(int32_t* x, int n, int delta, cudaStream_t stream);
+int convert_to_bf16(const void* src, int src_dtype, void* dst, int64_t n, cudaStream_t stream);
+// out[2I, h]: within each 128-row group g: rows [0,64) = gate[g*64 .. +64), rows [64,128) = up[g*64 .. +64)
+int interleave_gate_up(const void* gate, const void* up, void* out, int I, int h, cudaStream_t stream);
+int store_token(const int32_t* src, int32_t* dst_base, const int32_t* step_counter, int B, cudaStream_t stream);
+
+}  // namespace b2

@@ -1,0 +1,934 @@
+// Engine + C ABI of libb2llava.so: weight ingestion/repack, workspaces, and the orchestration of the
+// hot path (CLIP ViT -> mm_projector -> splice -> LLaMA prefill -> KV-cache decode) over the kernels in this
+// directory. Entry points are declared in include/b2llava.h, which cites the reference function each replaces.
+#include <cuda_fp16.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2llava.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2 {
+
+static thread_local char g_err[1024] = {0};
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+typedef __nv_bfloat16 bf16;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        free();
+        if (n == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+            return -2;
+        }
+        bytes = n;
+        return 0;
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct VitLayer {
+    DevBuf ln1_g, ln1_b, wqkv, bqkv, wo, bo, ln2_g, ln2_b, w1, b1, w2, b2;
+};
+struct LlamaLayer {
+    DevBuf ln1, wqkv, wo, ln2, wgu, wd;
+    DevBuf tmp_gate, tmp_up;  // staging until both halves arrived
+    bool has_gate = false, has_up = false;
+};
+}  // namespace
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_model {
+    b2_model_desc d;
+    int device = 0;
+    std::mutex mu;
+    bool finalized = false;
+    // derived
+    int P = 0, T = 0, kpad = 0, vit_live = 0, vit_hd = 64, hd = 128;
+    // weights
+    DevBuf patch_w, cls, pos, pre_g, pre_b;
+    std::vector<VitLayer> vit;
+    DevBuf p0_w, p0_b, p2_w, p2_b;
+    DevBuf embed, final_norm, lm_head;
+    std::vector<LlamaLayer> ll;
+    std::vector<std::string> seen;  // keys received (finalize checks completeness)
+    // ViT workspace (per chunk of max_images)
+    DevBuf v_col, v_patch, v_hidden, v_xn, v_qkv, v_attn, v_mlp, v_feats, p_mid;
+    // LLaMA workspace
+    DevBuf x, xn, qkv, attn, act, last_idx, xlast, logits;
+};
+
+struct b2_kv {
+    b2_model* m = nullptr;
+    int max_batch = 0, max_seq = 0;
+    DevBuf k, v;  // [L][B][H][Smax][D]
+    DevBuf len_dev, tok, step_counter, out_tokens, attn_partial, attn_counters;
+    std::vector<int32_t> len_host;
+    int out_capacity = 0;  // steps
+    // cached decode-step graph
+    cudaGraphExec_t graph = nullptr;
+    int graph_B = 0;
+    int warm_B = 0;  // an eager step has run for this B (function attributes set, driver entry points resolved)
+    size_t layer_stride() const { return (size_t)max_batch * m->d.heads * max_seq * m->hd; }
+};
+
+namespace {
+
+bool starts_with(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+
+// copy `n` elements of `dtype` from host-or-device `src` into bf16 device memory `dst` (contiguous)
+int ingest(const void* src, int dtype, void* dst, int64_t n, cudaStream_t st) {
+    if (dtype == DT_BF16) {
+        B2_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * 2, cudaMemcpyDefault, st));
+        B2_CUDA_CHECK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    const size_t esz = dtype == DT_F32 ? 4 : 2;
+    cudaPointerAttributes attr;
+    bool on_device = false;
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess)
+        on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    else
+        cudaGetLastError();
+    DevBuf tmp;
+    const void* dsrc = src;
+    if (!on_device) {
+        B2_TRY(tmp.alloc((size_t)n * esz));
+        B2_CUDA_CHECK(cudaMemcpy(tmp.p, src, (size_t)n * esz, cudaMemcpyDefault));
+        dsrc = tmp.p;
+    }
+    int r = convert_to_bf16(dsrc, dtype, dst, n, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    tmp.free();
+    if (r != 0) return r;
+    B2_CUDA_CHECK(e);
+    return 0;
+}
+
+int64_t numel(const int64_t* shape, int ndim) {
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    return n;
+}
+
+int expect_shape(const char* key, const int64_t* shape, int ndim, int64_t a, int64_t b = -1) {
+    const int64_t n = numel(shape, ndim);
+    const int64_t want = b < 0 ? a : a * b;
+    bool ok = n == want;
+    if (ok && b >= 0 && ndim >= 2) ok = shape[0] == a;
+    if (!ok) {
+        set_error("set_weight(%s): unexpected shape (numel %lld, expected %lld x %lld)", key, (long long)n,
+                  (long long)a, (long long)(b < 0 ? 1 : b));
+        return -1;
+    }
+    return 0;
+}
+
+// alloc-if-needed + ingest into dst buffer at element offset `off`
+int put(DevBuf& buf, size_t total_elems, size_t off, const void* src, int dtype, int64_t n) {
+    if (buf.p == nullptr) B2_TRY(buf.alloc(total_elems * 2));
+    return ingest(src, dtype, buf.as<bf16>() + off, n, 0);
+}
+
+int gemm(const void* A, int lda, const void* W, int ldw, const void* bias, const void* res, int ld_res, void* out,
+         int ld_out, int out_fp32, int M, int N, int K, int act, cudaStream_t st) {
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.residual = res; g.ld_res = ld_res;
+    g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.M = M; g.N = N; g.K = K; g.act = act;
+    return gemm_bf16(g, st);
+}
+
+int gemv(const void* x, int64_t ldx, const void* W, int ldw, const void* gamma, float eps, const void* res,
+         int ld_res, void* out, int ld_out, int out_fp32, int B, int N, int K, int act, cudaStream_t st) {
+    GemvArgs g;
+    g.x = x; g.ldx = ldx; g.W = W; g.ldw = ldw; g.norm_gamma = gamma; g.eps = eps; g.residual = res;
+    g.ld_res = ld_res; g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.B = B; g.N = N; g.K = K;
+    g.act = act;
+    return gemv_bf16(g, st);
+}
+
+int decode_nsplit(int B, int H) {
+    int n = (4 * num_sms() + B * H - 1) / (B * H);
+    if (n < 1) n = 1;
+    if (n > 32) n = 32;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight routing
+// ------------------------------------------------------------------------------------------------------
+int set_vision_weight(b2_model* m, const std::string& k, const void* ptr, const int64_t* shape, int ndim, int dt) {
+    const int D = m->d.vit_hidden, I = m->d.vit_inter;
+    const char* key = k.c_str();
+    if (k == "embeddings.class_embedding") {
+        B2_TRY(expect_shape(key, shape, ndim, D));
+        return put(m->cls, D, 0, ptr, dt, D);
+    }
+    if (k == "embeddings.patch_embedding.weight") {
+        const int kk = 3 * m->d.patch_size * m->d.patch_size;
+        B2_TRY(expect_shape(key, shape, ndim, D, kk));
+        // [D, 3, ps, ps] -> rows of kpad (zero padded) so the TMA row pitch is a multiple of 16 B
+        DevBuf tmp;
+        B2_TRY(tmp.alloc((size_t)D * kk * 2));
+        B2_TRY(ingest(ptr, dt, tmp.p, (int64_t)D * kk, 0));
+        if (m->patch_w.p == nullptr) B2_TRY(m->patch_w.alloc((size_t)D * m->kpad * 2));
+        B2_CUDA_CHECK(cudaMemset(m->patch_w.p, 0, (size_t)D * m->kpad * 2));
+        B2_CUDA_CHECK(cudaMemcpy2D(m->patch_w.p, (size_t)m->kpad * 2, tmp.p, (size_t)kk * 2, (size_t)kk * 2, D,
+                                   cudaMemcpyDeviceToDevice));
+        return 0;
+    }
+    if (k == "embeddings.position_embedding.weight") {
+        B2_TRY(expect_shape(key, shape, ndim, m->T, D));
+        return put(m->pos, (size_t)m->T * D, 0, ptr, dt, (int64_t)m->T * D);
+    }
+    if (k == "embeddings.position_ids") return 0;  // buffer in old checkpoints
+    if (k == "pre_layrnorm.weight") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(m->pre_g, D, 0, ptr, dt, D); }
+    if (k == "pre_layrnorm.bias") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(m->pre_b, D, 0, ptr, dt, D); }
+    if (starts_with(k, "post_layernorm.")) return 0;  // dead for select_layer=-2
+    if (starts_with(k, "encoder.layers.")) {
+        int li = -1, consumed = 0;
+        if (sscanf(key, "encoder.layers.%d.%n", &li, &consumed) != 1 || li < 0 || li >= m->d.vit_layers) {
+            set_error("set_weight: bad vision layer index in '%s'", key);
+            return -1;
+        }
+        if (li >= m->vit_live) return 0;  // layers above the selected hidden state are never computed
+        VitLayer& L = m->vit[li];
+        const std::string s = k.substr(consumed);
+        if (s == "layer_norm1.weight") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(L.ln1_g, D, 0, ptr, dt, D); }
+        if (s == "layer_norm1.bias") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(L.ln1_b, D, 0, ptr, dt, D); }
+        if (s == "layer_norm2.weight") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(L.ln2_g, D, 0, ptr, dt, D); }
+        if (s == "layer_norm2.bias") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(L.ln2_b, D, 0, ptr, dt, D); }
+        const char* names[3] = {"self_attn.q_proj.", "self_attn.k_proj.", "self_attn.v_proj."};
+        for (int j = 0; j < 3; ++j) {
+            if (starts_with(s, names[j])) {
+                if (s == std::string(names[j]) + "weight") {
+                    B2_TRY(expect_shape(key, shape, ndim, D, D));
+                    return put(L.wqkv, (size_t)3 * D * D, (size_t)j * D * D, ptr, dt, (int64_t)D * D);
+                }
+                B2_TRY(expect_shape(key, shape, ndim, D));
+                return put(L.bqkv, (size_t)3 * D, (size_t)j * D, ptr, dt, D);
+            }
+        }
+        if (s == "self_attn.out_proj.weight") { B2_TRY(expect_shape(key, shape, ndim, D, D)); return put(L.wo, (size_t)D * D, 0, ptr, dt, (int64_t)D * D); }
+        if (s == "self_attn.out_proj.bias") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(L.bo, D, 0, ptr, dt, D); }
+        if (s == "mlp.fc1.weight") { B2_TRY(expect_shape(key, shape, ndim, I, D)); return put(L.w1, (size_t)I * D, 0, ptr, dt, (int64_t)I * D); }
+        if (s == "mlp.fc1.bias") { B2_TRY(expect_shape(key, shape, ndim, I)); return put(L.b1, I, 0, ptr, dt, I); }
+        if (s == "mlp.fc2.weight") { B2_TRY(expect_shape(key, shape, ndim, D, I)); return put(L.w2, (size_t)D * I, 0, ptr, dt, (int64_t)D * I); }
+        if (s == "mlp.fc2.bias") { B2_TRY(expect_shape(key, shape, ndim, D)); return put(L.b2, D, 0, ptr, dt, D); }
+    }
+    set_error("set_weight: unknown vision key '%s'", key);
+    return -1;
+}
+
+int set_llama_layer_weight(b2_model* m, int li, const std::string& s, const char* key, const void* ptr,
+                           const int64_t* shape, int ndim, int dt) {
+    const int h = m->d.hidden, I = m->d.inter;
+    LlamaLayer& L = m->ll[li];
+    if (s == "input_layernorm.weight") { B2_TRY(expect_shape(key, shape, ndim, h)); return put(L.ln1, h, 0, ptr, dt, h); }
+    if (s == "post_attention_layernorm.weight") { B2_TRY(expect_shape(key, shape, ndim, h)); return put(L.ln2, h, 0, ptr, dt, h); }
+    const char* names[3] = {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight"};
+    for (int j = 0; j < 3; ++j) {
+        if (s == names[j]) {
+            B2_TRY(expect_shape(key, shape, ndim, h, h));
+            return put(L.wqkv, (size_t)3 * h * h, (size_t)j * h * h, ptr, dt, (int64_t)h * h);
+        }
+    }
+    if (s == "self_attn.o_proj.weight") { B2_TRY(expect_shape(key, shape, ndim, h, h)); return put(L.wo, (size_t)h * h, 0, ptr, dt, (int64_t)h * h); }
+    if (s == "mlp.down_proj.weight") { B2_TRY(expect_shape(key, shape, ndim, h, I)); return put(L.wd, (size_t)h * I, 0, ptr, dt, (int64_t)h * I); }
+    if (s == "mlp.gate_proj.weight" || s == "mlp.up_proj.weight") {
+        B2_TRY(expect_shape(key, shape, ndim, I, h));
+        const bool is_gate = s == "mlp.gate_proj.weight";
+        DevBuf& tmp = is_gate ? L.tmp_gate : L.tmp_up;
+        B2_TRY(put(tmp, (size_t)I * h, 0, ptr, dt, (int64_t)I * h));
+        (is_gate ? L.has_gate : L.has_up) = true;
+        if (L.has_gate && L.has_up) {
+            if (L.wgu.p == nullptr) B2_TRY(L.wgu.alloc((size_t)2 * I * h * 2));
+            B2_TRY(interleave_gate_up(L.tmp_gate.p, L.tmp_up.p, L.wgu.p, I, h, 0));
+            B2_CUDA_CHECK(cudaStreamSynchronize(0));
+            L.tmp_gate.free();
+            L.tmp_up.free();
+            L.has_gate = L.has_up = false;  // allow a later reload
+        }
+        return 0;
+    }
+    if (s == "self_attn.rotary_emb.inv_freq") return 0;  // buffer in 4.31-era checkpoints
+    set_error("set_weight: unknown decoder key '%s'", key);
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward passes (caller holds the model lock)
+// ------------------------------------------------------------------------------------------------------
+int vit_forward_chunk(b2_model* m, const void* pixels, int B, void* out_feats, cudaStream_t st) {
+    const b2_model_desc& d = m->d;
+    const int D = d.vit_hidden, I = d.vit_inter, H = d.vit_heads, P = m->P, T = m->T;
+    const int rows = B * T;
+    B2_TRY(vit_im2col(pixels, m->v_col.p, B, d.image_size, d.patch_size, m->kpad, st));
+    B2_TRY(gemm(m->v_col.p, m->kpad, m->patch_w.p, m->kpad, nullptr, nullptr, 0, m->v_patch.p, D, 0, B * P, D,
+                m->kpad, ACT_NONE, st));
+    B2_TRY(vit_embed_ln(m->v_patch.p, m->cls.p, m->pos.p, m->pre_g.p, m->pre_b.p, m->v_hidden.p, B, P, D,
+                        d.vit_ln_eps, st));
+    for (int l = 0; l < m->vit_live; ++l) {
+        VitLayer& L = m->vit[l];
+        B2_TRY(layernorm_bf16(m->v_hidden.p, L.ln1_g.p, L.ln1_b.p, m->v_xn.p, rows, D, d.vit_ln_eps, st));
+        B2_TRY(gemm(m->v_xn.p, D, L.wqkv.p, D, L.bqkv.p, nullptr, 0, m->v_qkv.p, 3 * D, 0, rows, 3 * D, D,
+                    ACT_NONE, st));
+        FlashArgs fa;
+        bf16* qkv = m->v_qkv.as<bf16>();
+        fa.q = qkv;         fa.q_bs = (int64_t)T * 3 * D; fa.q_ts = 3 * D; fa.q_hs = m->vit_hd;
+        fa.k = qkv + D;     fa.k_bs = fa.q_bs; fa.k_ts = 3 * D; fa.k_hs = m->vit_hd;
+        fa.v = qkv + 2 * D; fa.v_bs = fa.q_bs; fa.v_ts = 3 * D; fa.v_hs = m->vit_hd;
+        fa.o = m->v_attn.p; fa.o_bs = (int64_t)T * D; fa.o_ts = D; fa.o_hs = m->vit_hd;
+        fa.B = B; fa.H = H; fa.S = T; fa.D = m->vit_hd; fa.causal = 0;
+        fa.scale = 1.0f / sqrtf((float)m->vit_hd);
+        B2_TRY(flash_attn_bf16(fa, st));
+        B2_TRY(gemm(m->v_attn.p, D, L.wo.p, D, L.bo.p, m->v_hidden.p, D, m->v_hidden.p, D, 0, rows, D, D, ACT_NONE,
+                    st));
+        B2_TRY(layernorm_bf16(m->v_hidden.p, L.ln2_g.p, L.ln2_b.p, m->v_xn.p, rows, D, d.vit_ln_eps, st));
+        B2_TRY(gemm(m->v_xn.p, D, L.w1.p, D, L.b1.p, nullptr, 0, m->v_mlp.p, I, 0, rows, I, D, ACT_QUICK_GELU, st));
+        B2_TRY(gemm(m->v_mlp.p, I, L.w2.p, I, L.b2.p, m->v_hidden.p, D, m->v_hidden.p, D, 0, rows, D, I, ACT_NONE,
+                    st));
+    }
+    B2_TRY(vit_drop_cls(m->v_hidden.p, out_feats, B, P, D, st));
+    return 0;
+}
+
+int project_rows(b2_model* m, const void* feats, int rows, void* out, cudaStream_t st) {
+    const int D = m->d.vit_hidden, h = m->d.hidden;
+    const int max_rows = m->d.max_images * m->P;
+    for (int r0 = 0; r0 < rows; r0 += max_rows) {
+        const int n = rows - r0 < max_rows ? rows - r0 : max_rows;
+        const bf16* a = reinterpret_cast<const bf16*>(feats) + (size_t)r0 * D;
+        bf16* o = reinterpret_cast<bf16*>(out) + (size_t)r0 * h;
+        B2_TRY(gemm(a, D, m->p0_w.p, D, m->p0_b.p, nullptr, 0, m->p_mid.p, h, 0, n, h, D, ACT_GELU_ERF, st));
+        B2_TRY(gemm(m->p_mid.p, h, m->p2_w.p, h, m->p2_b.p, nullptr, 0, o, h, 0, n, h, h, ACT_NONE, st));
+    }
+    return 0;
+}
+
+// one decode step on kv-owned buffers: tok -> logits (m->logits) -> argmax -> tok, out_tokens[step], len += 1
+int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
+    const b2_model_desc& d = m->d;
+    const int h = d.hidden, I = d.inter, H = d.heads, V = d.vocab;
+    const int nsplit = decode_nsplit(B, H);
+    B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, st));
+    const bool small = B <= 8;
+    for (int l = 0; l < d.layers; ++l) {
+        LlamaLayer& L = m->ll[l];
+        if (small) {
+            B2_TRY(gemv(m->x.p, h, L.wqkv.p, h, L.ln1.p, d.rms_eps, nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h,
+                        ACT_NONE, st));
+        } else {
+            B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln1.p, m->xn.p, B, h, d.rms_eps, st));
+            B2_TRY(gemm(m->xn.p, h, L.wqkv.p, h, nullptr, nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h, ACT_NONE, st));
+        }
+        DecodeAttnArgs da;
+        da.qkv = m->qkv.p;
+        da.kcache = kv->k.as<bf16>() + (size_t)l * kv->layer_stride();
+        da.vcache = kv->v.as<bf16>() + (size_t)l * kv->layer_stride();
+        da.cur_len = kv->len_dev.as<int32_t>();
+        da.out = m->attn.p;
+        da.partial = kv->attn_partial.as<float>();
+        da.counters = kv->attn_counters.as<int32_t>();
+        da.B = B; da.H = H; da.D = m->hd; da.Smax = kv->max_seq; da.nsplit = nsplit;
+        da.theta = d.rope_theta;
+        da.scale = 1.0f / sqrtf((float)m->hd);
+        B2_TRY(decode_attn_bf16(da, st));
+        if (small) {
+            B2_TRY(gemv(m->attn.p, h, L.wo.p, h, nullptr, 0.f, m->x.p, h, m->x.p, h, 0, B, h, h, ACT_NONE, st));
+            B2_TRY(gemv(m->x.p, h, L.wgu.p, h, L.ln2.p, d.rms_eps, nullptr, 0, m->act.p, I, 0, B, 2 * I, h,
+                        ACT_SWIGLU, st));
+            B2_TRY(gemv(m->act.p, I, L.wd.p, I, nullptr, 0.f, m->x.p, h, m->x.p, h, 0, B, h, I, ACT_NONE, st));
+        } else {
+            B2_TRY(gemm(m->attn.p, h, L.wo.p, h, nullptr, m->x.p, h, m->x.p, h, 0, B, h, h, ACT_NONE, st));
+            B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln2.p, m->xn.p, B, h, d.rms_eps, st));
+            B2_TRY(gemm(m->xn.p, h, L.wgu.p, h, nullptr, nullptr, 0, m->act.p, I, 0, B, 2 * I, h, ACT_SWIGLU, st));
+            B2_TRY(gemm(m->act.p, I, L.wd.p, I, nullptr, m->x.p, h, m->x.p, h, 0, B, h, I, ACT_NONE, st));
+        }
+    }
+    if (small) {
+        B2_TRY(gemv(m->x.p, h, m->lm_head.p, h, m->final_norm.p, d.rms_eps, nullptr, 0, m->logits.p, V, 1, B, V, h,
+                    ACT_NONE, st));
+    } else {
+        B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, B, h, d.rms_eps, st));
+        B2_TRY(gemm(m->xn.p, h, m->lm_head.p, h, nullptr, nullptr, 0, m->logits.p, V, 1, B, V, h, ACT_NONE, st));
+    }
+    B2_TRY(argmax_f32(m->logits.as<float>(), B, V, kv->tok.as<int32_t>(), st));
+    B2_TRY(store_token(kv->tok.as<int32_t>(), kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), B, st));
+    B2_TRY(add_i32(kv->step_counter.as<int32_t>(), 1, 1, st));
+    B2_TRY(add_i32(kv->len_dev.as<int32_t>(), B, 1, st));
+    return 0;
+}
+
+// run one step, through the cached CUDA graph when possible
+int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
+    if (kv->warm_B != B) {
+        // first step for this batch size runs eagerly: sets function attributes, resolves driver entry points
+        if (kv->graph) { cudaGraphExecDestroy(kv->graph); kv->graph = nullptr; kv->graph_B = 0; }
+        B2_TRY(decode_step_launch(m, kv, B, st));
+        kv->warm_B = B;
+        return 0;
+    }
+    if (kv->graph == nullptr || kv->graph_B != B) {
+        if (kv->graph) { cudaGraphExecDestroy(kv->graph); kv->graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        B2_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long launches_before = g_launch_count;
+        int r = decode_step_launch(m, kv, B, st);
+        g_launch_count = launches_before;  // capture records launches, it does not run them
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+        B2_CUDA_CHECK(e);
+        e = cudaGraphInstantiate(&kv->graph, graph, 0);
+        cudaGraphDestroy(graph);
+        B2_CUDA_CHECK(e);
+        kv->graph_B = B;
+    }
+    B2_CUDA_CHECK(cudaGraphLaunch(kv->graph, st));
+    // kernels per step: embed + L*(qkv, attn, o, gate/up, down [+2 norms when B>8]) + head(+norm) + argmax + 3
+    const int per_layer = B <= 8 ? 5 : 7;
+    g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (B <= 8 ? 1 : 2) + 4;
+    return 0;
+}
+
+struct DeviceGuard {
+    explicit DeviceGuard(int dev) { cudaSetDevice(dev); }
+};
+
+}  // namespace
+
+// ==========================================================================================================
+// C ABI
+// ==========================================================================================================
+extern "C" {
+
+int b2_init(int device) {
+    B2_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("b2_init: device %d is sm_%d%d; this library only contains sm_100a code (no fallback path)", device,
+                  prop.major, prop.minor);
+        return -3;
+    }
+    return 0;
+}
+
+const char* b2_last_error(void) { return g_err; }
+int b2_version(void) { return 1; }
+unsigned long long b2_launch_count(void) { return g_launch_count; }
+
+int b2_model_create(const b2_model_desc* desc, b2_model** out) {
+    B2_CHECK_ARG(desc != nullptr && out != nullptr, "b2_model_create: null argument");
+    const b2_model_desc& d = *desc;
+    B2_CHECK_ARG(d.vit_hidden > 0 && d.vit_heads > 0 && d.vit_hidden / d.vit_heads == 64 &&
+                     d.vit_hidden % 256 == 0 && d.vit_hidden <= 2048,
+                 "b2_model_create: vision head_dim must be 64 and hidden a multiple of 256 (hidden=%d heads=%d)",
+                 d.vit_hidden, d.vit_heads);
+    B2_CHECK_ARG(d.hidden > 0 && d.heads > 0 && d.hidden / d.heads == 128 && d.hidden % 256 == 0,
+                 "b2_model_create: decoder head_dim must be 128 and hidden a multiple of 256 (hidden=%d heads=%d)",
+                 d.hidden, d.heads);
+    B2_CHECK_ARG(d.inter % 256 == 0 && d.vit_inter % 8 == 0 && d.vocab % 8 == 0,
+                 "b2_model_create: inter %% 256, vit_inter %% 8, vocab %% 8 must be 0");
+    B2_CHECK_ARG(d.image_size % d.patch_size == 0, "b2_model_create: image_size not a multiple of patch_size");
+    B2_CHECK_ARG(d.max_batch >= 1 && d.max_seq >= 1 && d.max_images >= 1, "b2_model_create: bad workspace sizing");
+    const int live = d.vit_select_layer < 0 ? d.vit_layers + 1 + d.vit_select_layer : d.vit_select_layer;
+    B2_CHECK_ARG(live >= 0 && live <= d.vit_layers, "b2_model_create: vit_select_layer %d out of range",
+                 d.vit_select_layer);
+    b2_model* m = new b2_model();
+    m->d = d;
+    cudaGetDevice(&m->device);
+    const int g = d.image_size / d.patch_size;
+    m->P = g * g;
+    m->T = m->P + 1;
+    const int kk = 3 * d.patch_size * d.patch_size;
+    m->kpad = (kk + 7) / 8 * 8;
+    m->vit_live = live;  // hidden_states[live] = output of encoder layer `live` (0 = embeddings)
+    m->vit.resize(live);
+    m->ll.resize(d.layers);
+    *out = m;
+    return 0;
+}
+
+int b2_model_set_weight(b2_model* m, const char* hf_key, const void* ptr, const int64_t* shape, int ndim, int dtype) {
+    B2_CHECK_ARG(m && hf_key && ptr && shape, "b2_model_set_weight: null argument");
+    B2_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16 || dtype == DT_F32, "b2_model_set_weight: bad dtype %d", dtype);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    std::string k(hf_key);
+    const int h = m->d.hidden, V = m->d.vocab, D = m->d.vit_hidden;
+    int r = -1;
+    size_t pos;
+    if ((pos = k.find("vision_model.")) != std::string::npos) {
+        r = set_vision_weight(m, k.substr(pos + strlen("vision_model.")), ptr, shape, ndim, dtype);
+    } else if (k == "model.embed_tokens.weight") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, V, h));
+        r = put(m->embed, (size_t)V * h, 0, ptr, dtype, (int64_t)V * h);
+    } else if (k == "model.norm.weight") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, h));
+        r = put(m->final_norm, h, 0, ptr, dtype, h);
+    } else if (k == "lm_head.weight") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, V, h));
+        r = put(m->lm_head, (size_t)V * h, 0, ptr, dtype, (int64_t)V * h);
+    } else if (k == "model.mm_projector.0.weight") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, h, D));
+        r = put(m->p0_w, (size_t)h * D, 0, ptr, dtype, (int64_t)h * D);
+    } else if (k == "model.mm_projector.0.bias") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, h));
+        r = put(m->p0_b, h, 0, ptr, dtype, h);
+    } else if (k == "model.mm_projector.2.weight") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, h, h));
+        r = put(m->p2_w, (size_t)h * h, 0, ptr, dtype, (int64_t)h * h);
+    } else if (k == "model.mm_projector.2.bias") {
+        B2_TRY(expect_shape(hf_key, shape, ndim, h));
+        r = put(m->p2_b, h, 0, ptr, dtype, h);
+    } else if (starts_with(k, "model.layers.")) {
+        int li = -1, consumed = 0;
+        if (sscanf(hf_key, "model.layers.%d.%n", &li, &consumed) != 1 || li < 0 || li >= m->d.layers) {
+            set_error("set_weight: bad decoder layer index in '%s'", hf_key);
+            return -1;
+        }
+        r = set_llama_layer_weight(m, li, k.substr(consumed), hf_key, ptr, shape, ndim, dtype);
+    } else {
+        set_error("set_weight: unknown key '%s'", hf_key);
+        return -1;
+    }
+    if (r == 0) m->seen.push_back(k);
+    return r;
+}
+
+int b2_model_finalize(b2_model* m) {
+    B2_CHECK_ARG(m != nullptr, "b2_model_finalize: null model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    const b2_model_desc& d = m->d;
+    // completeness
+    std::string missing;
+    auto need = [&](const DevBuf& b, const char* name) {
+        if (b.p == nullptr) { if (missing.size() < 600) { missing += name; missing += ' '; } }
+    };
+    need(m->patch_w, "patch_embedding"); need(m->cls, "class_embedding"); need(m->pos, "position_embedding");
+    need(m->pre_g, "pre_layrnorm.weight"); need(m->pre_b, "pre_layrnorm.bias");
+    for (size_t i = 0; i < m->vit.size(); ++i) {
+        VitLayer& L = m->vit[i];
+        const DevBuf* bs[12] = {&L.ln1_g, &L.ln1_b, &L.wqkv, &L.bqkv, &L.wo, &L.bo, &L.ln2_g, &L.ln2_b, &L.w1, &L.b1, &L.w2, &L.b2};
+        for (int j = 0; j < 12; ++j)
+            if (bs[j]->p == nullptr) { char t[64]; snprintf(t, sizeof t, "vision.layer%zu.#%d", i, j); need(*bs[j], t); }
+    }
+    need(m->p0_w, "mm_projector.0.weight"); need(m->p0_b, "mm_projector.0.bias");
+    need(m->p2_w, "mm_projector.2.weight"); need(m->p2_b, "mm_projector.2.bias");
+    need(m->embed, "embed_tokens"); need(m->final_norm, "model.norm"); need(m->lm_head, "lm_head");
+    for (size_t i = 0; i < m->ll.size(); ++i) {
+        LlamaLayer& L = m->ll[i];
+        const DevBuf* bs[6] = {&L.ln1, &L.wqkv, &L.wo, &L.ln2, &L.wgu, &L.wd};
+        for (int j = 0; j < 6; ++j)
+            if (bs[j]->p == nullptr) { char t[64]; snprintf(t, sizeof t, "layers.%zu.#%d", i, j); need(*bs[j], t); }
+    }
+    if (!missing.empty()) {
+        set_error("b2_model_finalize: missing weights: %s", missing.c_str());
+        return -3;
+    }
+    // q/k/v (and fused tensors filled piecewise) must each have received all parts: count keys
+    // (a partially filled fused buffer would contain uninitialised memory)
+    {
+        size_t want = 5 + m->vit.size() * 16 + 4 + 3 + m->ll.size() * 9;
+        size_t have = 0;
+        for (const std::string& k : m->seen)
+            if (k.find("post_layernorm") == std::string::npos && k.find("position_ids") == std::string::npos &&
+                k.find("inv_freq") == std::string::npos)
+                have++;
+        // keys for dead vision layers are accepted but not counted precisely; only flag clear shortfalls
+        if (have < want) {
+            set_error("b2_model_finalize: received %zu tensors, expected at least %zu", have, want);
+            return -3;
+        }
+    }
+    // workspaces
+    const int D = d.vit_hidden, I = d.vit_inter, h = d.hidden;
+    const size_t vrows = (size_t)d.max_images * m->T, prow = (size_t)d.max_images * m->P;
+    B2_TRY(m->v_col.alloc(prow * m->kpad * 2));
+    B2_TRY(m->v_patch.alloc(prow * D * 2));
+    B2_TRY(m->v_hidden.alloc(vrows * D * 2));
+    B2_TRY(m->v_xn.alloc(vrows * D * 2));
+    B2_TRY(m->v_qkv.alloc(vrows * 3 * D * 2));
+    B2_TRY(m->v_attn.alloc(vrows * D * 2));
+    B2_TRY(m->v_mlp.alloc(vrows * I * 2));
+    B2_TRY(m->v_feats.alloc(prow * D * 2));
+    B2_TRY(m->p_mid.alloc(prow * h * 2));
+    const size_t rows = (size_t)d.max_batch * d.max_seq;
+    B2_TRY(m->x.alloc(rows * h * 2));
+    B2_TRY(m->xn.alloc(rows * h * 2));
+    B2_TRY(m->qkv.alloc(rows * 3 * h * 2));
+    B2_TRY(m->attn.alloc(rows * h * 2));
+    B2_TRY(m->act.alloc(rows * d.inter * 2));
+    B2_TRY(m->last_idx.alloc((size_t)d.max_batch * 4));
+    B2_TRY(m->xlast.alloc((size_t)d.max_batch * h * 2));
+    B2_TRY(m->logits.alloc((size_t)d.max_batch * d.vocab * 4));
+    m->finalized = true;
+    return 0;
+}
+
+int b2_model_destroy(b2_model* m) {
+    if (m == nullptr) return 0;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    DevBuf* top[] = {&m->patch_w, &m->cls, &m->pos, &m->pre_g, &m->pre_b, &m->p0_w, &m->p0_b, &m->p2_w, &m->p2_b,
+                     &m->embed, &m->final_norm, &m->lm_head, &m->v_col, &m->v_patch, &m->v_hidden, &m->v_xn,
+                     &m->v_qkv, &m->v_attn, &m->v_mlp, &m->v_feats, &m->p_mid, &m->x, &m->xn, &m->qkv, &m->attn,
+                     &m->act, &m->last_idx, &m->xlast, &m->logits};
+    for (DevBuf* b : top) b->free();
+    for (VitLayer& L : m->vit) {
+        DevBuf* bs[12] = {&L.ln1_g, &L.ln1_b, &L.wqkv, &L.bqkv, &L.wo, &L.bo, &L.ln2_g, &L.ln2_b, &L.w1, &L.b1, &L.w2, &L.b2};
+        for (DevBuf* b : bs) b->free();
+    }
+    for (LlamaLayer& L : m->ll) {
+        DevBuf* bs[8] = {&L.ln1, &L.wqkv, &L.wo, &L.ln2, &L.wgu, &L.wd, &L.tmp_gate, &L.tmp_up};
+        for (DevBuf* b : bs) b->free();
+    }
+    delete m;
+    return 0;
+}
+
+int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
+    B2_CHECK_ARG(m && out, "b2_kv_create: null argument");
+    B2_CHECK_ARG(max_batch >= 1 && max_batch <= m->d.max_batch, "b2_kv_create: max_batch %d exceeds model max_batch %d",
+                 max_batch, m->d.max_batch);
+    B2_CHECK_ARG(max_seq >= 1, "b2_kv_create: max_seq must be positive");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    b2_kv* kv = new b2_kv();
+    kv->m = m;
+    kv->max_batch = max_batch;
+    kv->max_seq = max_seq;
+    const size_t per = (size_t)m->d.layers * kv->layer_stride() * 2;
+    int r = 0;
+    if ((r = kv->k.alloc(per)) != 0 || (r = kv->v.alloc(per)) != 0 ||
+        (r = kv->len_dev.alloc((size_t)max_batch * 4)) != 0 || (r = kv->tok.alloc((size_t)max_batch * 4)) != 0 ||
+        (r = kv->step_counter.alloc(4)) != 0) {
+        b2_kv_destroy(kv);
+        return r;
+    }
+    kv->out_capacity = max_seq;
+    const int max_split = 32;
+    if ((r = kv->out_tokens.alloc((size_t)kv->out_capacity * max_batch * 4)) != 0 ||
+        (r = kv->attn_partial.alloc((size_t)max_batch * m->d.heads * max_split * (128 + 2) * 4)) != 0 ||
+        (r = kv->attn_counters.alloc((size_t)max_batch * m->d.heads * 4)) != 0) {
+        b2_kv_destroy(kv);
+        return r;
+    }
+    cudaMemset(kv->k.p, 0, per);
+    cudaMemset(kv->v.p, 0, per);
+    cudaMemset(kv->len_dev.p, 0, (size_t)max_batch * 4);
+    cudaMemset(kv->tok.p, 0, (size_t)max_batch * 4);
+    cudaMemset(kv->step_counter.p, 0, 4);
+    cudaMemset(kv->attn_counters.p, 0, (size_t)max_batch * m->d.heads * 4);
+    kv->len_host.assign(max_batch, 0);
+    *out = kv;
+    return 0;
+}
+
+int b2_kv_reset(b2_kv* kv) {
+    B2_CHECK_ARG(kv != nullptr, "b2_kv_reset: null");
+    std::lock_guard<std::mutex> lk(kv->m->mu);
+    DeviceGuard dg(kv->m->device);
+    B2_CUDA_CHECK(cudaMemset(kv->len_dev.p, 0, (size_t)kv->max_batch * 4));
+    B2_CUDA_CHECK(cudaMemset(kv->step_counter.p, 0, 4));
+    kv->len_host.assign(kv->max_batch, 0);
+    return 0;
+}
+
+int b2_kv_destroy(b2_kv* kv) {
+    if (kv == nullptr) return 0;
+    cudaSetDevice(kv->m->device);
+    cudaDeviceSynchronize();
+    if (kv->graph) cudaGraphExecDestroy(kv->graph);
+    DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
+                    &kv->attn_counters};
+    for (DevBuf* b : bs) b->free();
+    delete kv;
+    return 0;
+}
+
+int b2_kv_lengths(b2_kv* kv, int32_t* lens_host, int n) {
+    B2_CHECK_ARG(kv && lens_host && n >= 0 && n <= kv->max_batch, "b2_kv_lengths: bad argument");
+    for (int i = 0; i < n; ++i) lens_host[i] = kv->len_host[i];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int b2_vit_encode(b2_model* m, const void* pixels, int B, void* out_feats, void* stream) {
+    B2_CHECK_ARG(m && pixels && out_feats && B >= 1, "b2_vit_encode: bad argument");
+    B2_CHECK_ARG(m->finalized, "b2_vit_encode: model not finalized");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t img_elems = (size_t)3 * m->d.image_size * m->d.image_size;
+    for (int b0 = 0; b0 < B; b0 += m->d.max_images) {
+        const int n = B - b0 < m->d.max_images ? B - b0 : m->d.max_images;
+        B2_TRY(vit_forward_chunk(m, reinterpret_cast<const bf16*>(pixels) + b0 * img_elems, n,
+                                 reinterpret_cast<bf16*>(out_feats) + (size_t)b0 * m->P * m->d.vit_hidden, st));
+    }
+    return 0;
+}
+
+int b2_project(b2_model* m, const void* feats, int rows, void* out, void* stream) {
+    B2_CHECK_ARG(m && feats && out && rows >= 1, "b2_project: bad argument");
+    B2_CHECK_ARG(m->finalized, "b2_project: model not finalized");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    return project_rows(m, feats, rows, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* stream) {
+    B2_CHECK_ARG(m && pixels && out && B >= 1, "b2_encode_images: bad argument");
+    B2_CHECK_ARG(m->finalized, "b2_encode_images: model not finalized");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t img_elems = (size_t)3 * m->d.image_size * m->d.image_size;
+    for (int b0 = 0; b0 < B; b0 += m->d.max_images) {
+        const int n = B - b0 < m->d.max_images ? B - b0 : m->d.max_images;
+        B2_TRY(vit_forward_chunk(m, reinterpret_cast<const bf16*>(pixels) + b0 * img_elems, n, m->v_feats.p, st));
+        B2_TRY(project_rows(m, m->v_feats.p, n * m->P,
+                            reinterpret_cast<bf16*>(out) + (size_t)b0 * m->P * m->d.hidden, st));
+    }
+    return 0;
+}
+
+int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, int rows, void* embeds_out,
+              void* stream) {
+    B2_CHECK_ARG(m && src_index && embeds_out && rows >= 1, "b2_splice: bad argument");
+    B2_CHECK_ARG(m->finalized, "b2_splice: model not finalized");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    return splice_embed(src_index, m->embed.p, image_feats, embeds_out, rows, m->d.hidden,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_lens_host, int B, int S,
+               void* logits_out, int logits_mode, void* stream) {
+    B2_CHECK_ARG(m && kv && embeds && kv->m == m, "b2_prefill: bad handle");
+    B2_CHECK_ARG(m->finalized, "b2_prefill: model not finalized");
+    B2_CHECK_ARG(B >= 1 && B <= kv->max_batch && S >= 1 && S <= kv->max_seq,
+                 "b2_prefill: B=%d S=%d exceed the KV cache (max_batch=%d max_seq=%d)", B, S, kv->max_batch, kv->max_seq);
+    B2_CHECK_ARG((size_t)B * S <= (size_t)m->d.max_batch * m->d.max_seq,
+                 "b2_prefill: B*S=%d exceeds the workspace (%d rows)", B * S, m->d.max_batch * m->d.max_seq);
+    B2_CHECK_ARG(logits_mode == B2_LOGITS_NONE || logits_out != nullptr, "b2_prefill: logits_out is null");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const b2_model_desc& d = m->d;
+    const int h = d.hidden, I = d.inter, H = d.heads, V = d.vocab, T = B * S;
+
+    std::vector<int32_t> lens(B), last(B);
+    for (int b = 0; b < B; ++b) {
+        lens[b] = seq_lens_host ? seq_lens_host[b] : S;
+        B2_CHECK_ARG(lens[b] >= 1 && lens[b] <= S, "b2_prefill: seq_lens[%d]=%d out of range (S=%d)", b, lens[b], S);
+        last[b] = b * S + lens[b] - 1;
+    }
+    B2_CUDA_CHECK(cudaMemcpyAsync(kv->len_dev.p, lens.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA_CHECK(cudaMemcpyAsync(m->last_idx.p, last.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));  // lens/last are stack-backed host vectors
+    for (int b = 0; b < B; ++b) kv->len_host[b] = lens[b];
+
+    B2_CUDA_CHECK(cudaMemcpyAsync(m->x.p, embeds, (size_t)T * h * 2, cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < d.layers; ++l) {
+        LlamaLayer& L = m->ll[l];
+        bf16* kc = kv->k.as<bf16>() + (size_t)l * kv->layer_stride();
+        bf16* vc = kv->v.as<bf16>() + (size_t)l * kv->layer_stride();
+        B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln1.p, m->xn.p, T, h, d.rms_eps, st));
+        B2_TRY(gemm(m->xn.p, h, L.wqkv.p, h, nullptr, nullptr, 0, m->qkv.p, 3 * h, 0, T, 3 * h, h, ACT_NONE, st));
+        B2_TRY(rope_kv_write(m->qkv.p, kc, vc, B, S, H, m->hd, kv->max_seq, d.rope_theta, st));
+        FlashArgs fa;
+        fa.q = m->qkv.p; fa.q_bs = (int64_t)S * 3 * h; fa.q_ts = 3 * h; fa.q_hs = m->hd;
+        fa.k = kc; fa.k_bs = (int64_t)H * kv->max_seq * m->hd; fa.k_ts = m->hd; fa.k_hs = (int64_t)kv->max_seq * m->hd;
+        fa.v = vc; fa.v_bs = fa.k_bs; fa.v_ts = m->hd; fa.v_hs = fa.k_hs;
+        fa.o = m->attn.p; fa.o_bs = (int64_t)S * h; fa.o_ts = h; fa.o_hs = m->hd;
+        fa.seq_lens = kv->len_dev.as<int32_t>();
+        fa.B = B; fa.H = H; fa.S = S; fa.D = m->hd; fa.causal = 1;
+        fa.scale = 1.0f / sqrtf((float)m->hd);
+        B2_TRY(flash_attn_bf16(fa, st));
+        B2_TRY(gemm(m->attn.p, h, L.wo.p, h, nullptr, m->x.p, h, m->x.p, h, 0, T, h, h, ACT_NONE, st));
+        B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln2.p, m->xn.p, T, h, d.rms_eps, st));
+        B2_TRY(gemm(m->xn.p, h, L.wgu.p, h, nullptr, nullptr, 0, m->act.p, I, 0, T, 2 * I, h, ACT_SWIGLU, st));
+        B2_TRY(gemm(m->act.p, I, L.wd.p, I, nullptr, m->x.p, h, m->x.p, h, 0, T, h, I, ACT_NONE, st));
+    }
+    if (logits_mode == B2_LOGITS_LAST) {
+        // only the last valid position per sample feeds generation (the reference computes lm_head on all S)
+        B2_TRY(rmsnorm_gather_bf16(m->x.p, m->last_idx.as<int32_t>(), m->final_norm.p, m->xlast.p, B, h, d.rms_eps, st));
+        if (B <= 8)
+            B2_TRY(gemv(m->xlast.p, h, m->lm_head.p, h, nullptr, 0.f, nullptr, 0, logits_out, V, 1, B, V, h, ACT_NONE, st));
+        else
+            B2_TRY(gemm(m->xlast.p, h, m->lm_head.p, h, nullptr, nullptr, 0, logits_out, V, 1, B, V, h, ACT_NONE, st));
+    } else if (logits_mode == B2_LOGITS_ALL) {
+        B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, T, h, d.rms_eps, st));
+        B2_TRY(gemm(m->xn.p, h, m->lm_head.p, h, nullptr, nullptr, 0, logits_out, V, 1, T, V, h, ACT_NONE, st));
+    }
+    return 0;
+}
+
+static int copy_tokens_in(b2_kv* kv, const int32_t* tokens, int B, cudaStream_t st) {
+    B2_CUDA_CHECK(cudaMemcpyAsync(kv->tok.p, tokens, (size_t)B * 4, cudaMemcpyDefault, st));
+    return 0;
+}
+
+int b2_decode_step(b2_model* m, b2_kv* kv, const int32_t* tokens, int B, void* logits_out, int32_t* next_tokens_out,
+                   void* stream) {
+    B2_CHECK_ARG(m && kv && tokens && kv->m == m, "b2_decode_step: bad handle");
+    B2_CHECK_ARG(m->finalized, "b2_decode_step: model not finalized");
+    B2_CHECK_ARG(B >= 1 && B <= kv->max_batch, "b2_decode_step: B=%d exceeds cache batch %d", B, kv->max_batch);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int b = 0; b < B; ++b)
+        B2_CHECK_ARG(kv->len_host[b] >= 1 && kv->len_host[b] < kv->max_seq,
+                     "b2_decode_step: sample %d has cache length %d (capacity %d; prefill first)", b, kv->len_host[b],
+                     kv->max_seq);
+    B2_TRY(copy_tokens_in(kv, tokens, B, st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
+    B2_TRY(decode_step_run(m, kv, B, st));
+    for (int b = 0; b < B; ++b) kv->len_host[b]++;
+    if (logits_out)
+        B2_CUDA_CHECK(cudaMemcpyAsync(logits_out, m->logits.p, (size_t)B * m->d.vocab * 4, cudaMemcpyDefault, st));
+    if (next_tokens_out) {
+        B2_CUDA_CHECK(cudaMemcpyAsync(next_tokens_out, kv->tok.p, (size_t)B * 4, cudaMemcpyDefault, st));
+        B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int b2_decode_greedy(b2_model* m, b2_kv* kv, const int32_t* first_tokens, int B, int n_steps, int32_t* out_tokens,
+                     void* stream) {
+    B2_CHECK_ARG(m && kv && first_tokens && out_tokens && kv->m == m, "b2_decode_greedy: bad handle");
+    B2_CHECK_ARG(m->finalized, "b2_decode_greedy: model not finalized");
+    B2_CHECK_ARG(B >= 1 && B <= kv->max_batch && n_steps >= 1, "b2_decode_greedy: bad B=%d n_steps=%d", B, n_steps);
+    B2_CHECK_ARG(n_steps <= kv->out_capacity, "b2_decode_greedy: n_steps=%d exceeds capacity %d", n_steps,
+                 kv->out_capacity);
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int b = 0; b < B; ++b)
+        B2_CHECK_ARG(kv->len_host[b] >= 1 && kv->len_host[b] + n_steps <= kv->max_seq,
+                     "b2_decode_greedy: sample %d cache length %d + %d steps exceeds capacity %d", b, kv->len_host[b],
+                     n_steps, kv->max_seq);
+    B2_TRY(copy_tokens_in(kv, first_tokens, B, st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
+    for (int s = 0; s < n_steps; ++s) B2_TRY(decode_step_run(m, kv, B, st));
+    for (int b = 0; b < B; ++b) kv->len_host[b] += n_steps;
+    B2_CUDA_CHECK(cudaMemcpyAsync(out_tokens, kv->out_tokens.p, (size_t)n_steps * B * 4, cudaMemcpyDefault, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b2_argmax(const float* logits, int B, int V, int32_t* out, void* stream) {
+    B2_CHECK_ARG(logits && out, "b2_argmax: null argument");
+    return argmax_f32(logits, B, V, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// single-kernel entry points
+// ---------------------------------------------------------------------------------------------------------
+int b2_op_gemm(const void* A, int lda, const void* W, int ldw, const void* bias, const void* residual, int ld_res,
+               void* out, int ld_out, int out_fp32, int M, int N, int K, int act, int bn_override, void* stream) {
+    B2_CHECK_ARG(A && W && out, "b2_op_gemm: null argument");
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.residual = residual; g.ld_res = ld_res;
+    g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.M = M; g.N = N; g.K = K; g.act = act;
+    g.bn_override = bn_override;
+    return gemm_bf16(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_gemv(const void* x, int64_t ldx, const void* W, int ldw, const void* norm_gamma, float eps,
+               const void* residual, int ld_res, void* out, int ld_out, int out_fp32, int B, int N, int K, int act,
+               void* stream) {
+    B2_CHECK_ARG(x && W && out, "b2_op_gemv: null argument");
+    return gemv(x, ldx, W, ldw, norm_gamma, eps, residual, ld_res, out, ld_out, out_fp32, B, N, K, act,
+                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,
+                    void* stream) {
+    B2_CHECK_ARG(x && gamma && beta && y, "b2_op_layernorm: null argument");
+    return layernorm_bf16(x, gamma, beta, y, rows, cols, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_rmsnorm(const void* x, const void* gamma, void* y, int rows, int cols, float eps, void* stream) {
+    B2_CHECK_ARG(x && gamma && y, "b2_op_rmsnorm: null argument");
+    return rmsnorm_bf16(x, cols, gamma, y, rows, cols, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_flash_attn(const void* q, const void* k, const void* v, void* o, const int32_t* seq_lens, int B, int S,
+                     int H, int D, int causal, float scale, void* stream) {
+    B2_CHECK_ARG(q && k && v && o, "b2_op_flash_attn: null argument");
+    FlashArgs fa;
+    const int64_t ts = (int64_t)H * D, bs = (int64_t)S * H * D;
+    fa.q = q; fa.q_bs = bs; fa.q_ts = ts; fa.q_hs = D;
+    fa.k = k; fa.k_bs = bs; fa.k_ts = ts; fa.k_hs = D;
+    fa.v = v; fa.v_bs = bs; fa.v_ts = ts; fa.v_hs = D;
+    fa.o = o; fa.o_bs = bs; fa.o_ts = ts; fa.o_hs = D;
+    fa.seq_lens = seq_lens; fa.B = B; fa.H = H; fa.S = S; fa.D = D; fa.causal = causal; fa.scale = scale;
+    return flash_attn_bf16(fa, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, int D, int Smax, float theta,
+                        void* stream) {
+    B2_CHECK_ARG(qkv && kcache && vcache, "b2_op_rope_kv_write: null argument");
+    return rope_kv_write(qkv, kcache, vcache, B, S, H, D, Smax, theta, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t b2_op_decode_attn_scratch_bytes(int B, int H, int nsplit) {
+    return (int64_t)B * H * 4 /*counters*/ + 256 + (int64_t)B * H * nsplit * (128 + 2) * 4;
+}
+
+int b2_op_decode_attn(const void* qkv, void* kcache, void* vcache, const int32_t* cur_len, void* out, void* scratch,
+                      int B, int H, int Smax, int nsplit, float theta, float scale, void* stream) {
+    B2_CHECK_ARG(qkv && kcache && vcache && cur_len && out && scratch, "b2_op_decode_attn: null argument");
+    DecodeAttnArgs da;
+    da.qkv = qkv; da.kcache = kcache; da.vcache = vcache; da.cur_len = cur_len; da.out = out;
+    da.counters = reinterpret_cast<int32_t*>(scratch);
+    const size_t off = ((size_t)B * H * 4 + 255) / 256 * 256;
+    da.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + off);
+    da.B = B; da.H = H; da.D = 128; da.Smax = Smax; da.nsplit = nsplit; da.theta = theta; da.scale = scale;
+    return decode_attn_bf16(da, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_interleave_gate_up(const void* gate, const void* up, void* out, int I, int h, void* stream) {
+    B2_CHECK_ARG(gate && up && out, "b2_op_interleave_gate_up: null argument");
+    return interleave_gate_up(gate, up, out, I, h, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_op_im2col(const void* pixels, void* out, int B, int img, int patch, int kpad, void* stream) {
+    B2_CHECK_ARG(pixels && out, "b2_op_im2col: null argument");
+    return vit_im2col(pixels, out, B, img, patch, kpad, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
