@@ -126,7 +126,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t"
             ".reg .pred P;\n\t"
@@ -134,7 +134,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, P;\n\t"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(100000u)
+            : "r"(addr), "r"(parity), "r"(1000u)
             : "memory");
         if (done) return;
     }

@@ -1,0 +1,428 @@
+"""LlavaLlamaForCausalLM on the B200 engine.
+
+Same public surface as the reference's llava/model/language_model/llava_llama.py (LlavaConfig :29-30,
+LlavaLlamaModel :33-38, LlavaLlamaForCausalLM.forward :56-99, prepare_inputs_for_generation :101-108) and
+the same state-dict key layout, so `load_pretrained_model`, `llava.serve.model_worker`,
+`llava.serve.cli` and the eval scripts can drive it unchanged. The modules here only HOLD checkpoint tensors;
+all arithmetic of the path (CLIP ViT, projector, splice, LLaMA prefill + KV-cache decode, lm_head, greedy
+argmax) runs in libb2llava.so through the C ABI in include/b2llava.h. There is no PyTorch fallback: without
+the CUDA library / an sm_100 device every compute entry point raises.
+
+Compute dtype is bf16 (north-star). Callers that ask for fp16 (`.half()`, torch_dtype=float16 in the
+reference's builder.py:43) keep their tensor dtypes at the boundary, the engine computes in bf16.
+"""
+import json
+import os
+import weakref
+from typing import List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from transformers import AutoConfig, LlamaConfig
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+from ..llava_arch import LlavaMetaModel, LlavaMetaForCausalLM
+from ..multimodal_encoder.clip_encoder import _Holder, _read_checkpoint_dir
+from ..._b2 import Engine, KVCache, LOGITS_ALL, LOGITS_LAST
+
+
+class LlavaConfig(LlamaConfig):
+    model_type = "llava"
+
+
+def _empty_param(*shape, dtype=None, device=None):
+    return nn.Parameter(torch.empty(*shape, dtype=dtype, device=device), requires_grad=False)
+
+
+class _Weight(nn.Module):
+    """`<name>.weight` holder (Linear without bias / RMSNorm / Embedding), never initialised on construction."""
+
+    def __init__(self, *shape, dtype=None, device=None):
+        super().__init__()
+        self.weight = _empty_param(*shape, dtype=dtype, device=device)
+
+
+class _DecoderWeights(nn.Module):
+    """State-dict layout of transformers LlamaModel: embed_tokens, layers.N.{self_attn,mlp,*_layernorm}, norm."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        h, I, V = config.hidden_size, config.intermediate_size, config.vocab_size
+        dt = getattr(config, "_b2_param_dtype", torch.bfloat16)
+        dev = getattr(config, "_b2_param_device", None)
+        self.embed_tokens = _Weight(V, h, dtype=dt, device=dev)
+        layers = []
+        for _ in range(config.num_hidden_layers):
+            L = _Holder()
+            L.self_attn = _Holder()
+            for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                setattr(L.self_attn, n, _Weight(h, h, dtype=dt, device=dev))
+            L.mlp = _Holder()
+            L.mlp.gate_proj = _Weight(I, h, dtype=dt, device=dev)
+            L.mlp.up_proj = _Weight(I, h, dtype=dt, device=dev)
+            L.mlp.down_proj = _Weight(h, I, dtype=dt, device=dev)
+            L.input_layernorm = _Weight(h, dtype=dt, device=dev)
+            L.post_attention_layernorm = _Weight(h, dtype=dt, device=dev)
+            layers.append(L)
+        self.layers = nn.ModuleList(layers)
+        self.norm = _Weight(h, dtype=dt, device=dev)
+
+
+class LlavaLlamaModel(LlavaMetaModel, _DecoderWeights):
+    config_class = LlavaConfig
+
+    def __init__(self, config):
+        super(LlavaLlamaModel, self).__init__(config)
+
+
+class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
+    config_class = LlavaConfig
+
+    def __init__(self, config, device=None, dtype=torch.bfloat16, max_batch=None, max_seq=None, max_images=None):
+        nn.Module.__init__(self)
+        if getattr(config, "num_key_value_heads", config.num_attention_heads) != config.num_attention_heads:
+            raise NotImplementedError("grouped-query attention is not part of the LLaVA-1.5 path (kv_heads == heads)")
+        if getattr(config, "pretraining_tp", 1) != 1:
+            raise NotImplementedError("pretraining_tp != 1")
+        self.config = config
+        config._b2_param_dtype, config._b2_param_device = dtype, device
+        try:
+            self.model = LlavaLlamaModel(config)
+        finally:
+            del config._b2_param_dtype, config._b2_param_device
+        self.vocab_size = config.vocab_size
+        self.lm_head = _Weight(config.vocab_size, config.hidden_size, dtype=dtype, device=device)
+        self._engine = None
+        self._kv = None
+        self._limits = {"max_batch": max_batch, "max_seq": max_seq, "max_images": max_images}
+        self._attach()
+
+    # ------------------------------------------------------------------ plumbing
+    def _attach(self):
+        ref = weakref.ref(self)
+        self.model._owner = ref
+        if getattr(self.model, "mm_projector", None) is not None:
+            self.model.mm_projector._owner = ref
+        vt = self.model.get_vision_tower()
+        if vt is not None:
+            vt._owner = ref
+
+    def get_model(self):
+        return self.model
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    @property
+    def device(self):
+        return self.lm_head.weight.device
+
+    @property
+    def dtype(self):
+        return self.lm_head.weight.dtype
+
+    def invalidate_engine(self):
+        """Weights changed (load_state_dict, resize, tower load): rebuild the device engine lazily."""
+        self._kv = None
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self.invalidate_engine()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self.invalidate_engine()
+        return r
+
+    def resize_token_embeddings(self, new_num_tokens=None):
+        old = self.model.embed_tokens.weight
+        if new_num_tokens is None or new_num_tokens == old.shape[0]:
+            return self.model.embed_tokens
+        for mod in (self.model.embed_tokens, self.lm_head):
+            w = mod.weight.data
+            nw = torch.zeros(new_num_tokens, w.shape[1], dtype=w.dtype, device=w.device)
+            n = min(new_num_tokens, w.shape[0])
+            nw[:n] = w[:n]
+            if new_num_tokens > n:
+                nw[n:].normal_(mean=0.0, std=getattr(self.config, "initializer_range", 0.02))
+            mod.weight = nn.Parameter(nw, requires_grad=False)
+        self.config.vocab_size = self.vocab_size = new_num_tokens
+        self.invalidate_engine()
+        return self.model.embed_tokens
+
+    def engine_limits(self, max_batch=None, max_seq=None, max_images=None):
+        """Workspace sizing of the device engine (KV cache + activations); call before the first forward."""
+        for k, v in (("max_batch", max_batch), ("max_seq", max_seq), ("max_images", max_images)):
+            if v is not None and v != self._limits[k]:
+                self._limits[k] = v
+                self.invalidate_engine()
+
+    def _ensure_engine(self) -> Engine:
+        if self._engine is not None:
+            return self._engine
+        vt = self.get_vision_tower()
+        if vt is None or not vt.is_loaded:
+            raise RuntimeError("vision tower is not loaded: call model.get_vision_tower().load_model() first")
+        if self.device.type != "cuda":
+            raise RuntimeError("LlavaLlamaForCausalLM weights must be on a CUDA (sm_100a) device: model.to('cuda'); "
+                               "there is no CPU path")
+        c, vc = self.config, vt.config
+        max_seq = self._limits["max_seq"] or min(getattr(c, "max_position_embeddings", 4096), 4096)
+        desc = dict(
+            image_size=vc.image_size, patch_size=vc.patch_size, vit_hidden=vc.hidden_size,
+            vit_inter=vc.intermediate_size, vit_layers=vc.num_hidden_layers, vit_heads=vc.num_attention_heads,
+            vit_select_layer=vt.select_layer, vit_ln_eps=vc.layer_norm_eps,
+            hidden=c.hidden_size, inter=c.intermediate_size, layers=c.num_hidden_layers,
+            heads=c.num_attention_heads, vocab=self.lm_head.weight.shape[0], rms_eps=c.rms_norm_eps,
+            rope_theta=float(getattr(c, "rope_theta", None) or (getattr(c, "rope_parameters", None) or {}).get("rope_theta", 10000.0)),
+            max_batch=self._limits["max_batch"] or 1, max_seq=max_seq, max_images=self._limits["max_images"] or 8,
+        )
+        if getattr(vc, "hidden_act", "quick_gelu") != "quick_gelu":
+            raise NotImplementedError("CLIP tower activation must be quick_gelu (openai/clip-vit-large-patch14-336)")
+        eng = Engine(desc, self.device)
+        for k, v in self.state_dict().items():
+            if "position_ids" in k or "inv_freq" in k:
+                continue
+            eng.set_weight(k, v.to(self.device))
+        eng.finalize()
+        self._engine = eng
+        self._kv = None
+        return eng
+
+    def _get_kv(self, B, need_seq):
+        eng = self._ensure_engine()
+        lim_b, lim_s = eng.desc.max_batch, eng.desc.max_seq
+        if B > lim_b or need_seq > lim_s:
+            raise ValueError(f"batch {B} / sequence {need_seq} exceed the engine limits (max_batch={lim_b}, max_seq={lim_s}); "
+                             f"call model.engine_limits(max_batch=..., max_seq=...) before the first forward")
+        if self._kv is None:
+            self._kv = eng.new_kv(lim_b, lim_s)
+        return self._kv
+
+    # ------------------------------------------------------------------ forward (ref llava_llama.py:56-99)
+    def forward(
+        self,
+        input_ids: torch.LongTensor = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        position_ids: Optional[torch.LongTensor] = None,
+        past_key_values=None,
+        inputs_embeds: Optional[torch.FloatTensor] = None,
+        labels: Optional[torch.LongTensor] = None,
+        use_cache: Optional[bool] = None,
+        output_attentions: Optional[bool] = None,
+        output_hidden_states: Optional[bool] = None,
+        images: Optional[torch.FloatTensor] = None,
+        return_dict: Optional[bool] = None,
+    ) -> Union[Tuple, CausalLMOutputWithPast]:
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention maps / hidden states are never materialised on the fused path")
+        engine = self._ensure_engine()
+
+        # ---- decode step: [B,1] ids against an engine cache ----
+        if inputs_embeds is None and past_key_values is not None and input_ids is not None and input_ids.shape[1] == 1:
+            if not isinstance(past_key_values, KVCache):
+                raise ValueError("past_key_values must be the cache object returned by a previous forward of this model")
+            logits = engine.decode_step(past_key_values, input_ids.reshape(-1))
+            logits = logits.unsqueeze(1)
+            return self._output(logits, past_key_values, labels, return_dict)
+
+        if inputs_embeds is None:
+            (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels) = \
+                self.prepare_inputs_labels_for_multimodal(input_ids, position_ids, attention_mask, past_key_values, labels, images)
+            if inputs_embeds is None:  # text-only (no images / no tower): plain embedding lookup on the engine
+                ids = input_ids.to(torch.int32).reshape(-1).to(engine.device)
+                inputs_embeds = engine.splice(ids, None, input_ids.shape[0], input_ids.shape[1])
+        if past_key_values is not None:
+            raise NotImplementedError("chunked prefill against an existing cache is not part of the reference's call pattern")
+
+        B, S = inputs_embeds.shape[0], inputs_embeds.shape[1]
+        lens, left = None, False
+        if attention_mask is not None:
+            m = attention_mask.to(device=inputs_embeds.device).bool()
+            lens = m.sum(dim=1).tolist()
+            left = bool((~m[:, 0]).any()) and bool(m[:, -1].all())
+            if left:  # engine rows are right-padded: rotate valid tokens to the front (ref pads left only on request)
+                inputs_embeds = torch.stack([torch.roll(inputs_embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
+        kv = self._get_kv(B, S)
+        kv.reset()
+        logits = engine.prefill(kv, inputs_embeds, lens, LOGITS_ALL)
+        if left:
+            logits = torch.stack([torch.roll(logits[b], shifts=(S - lens[b]), dims=0) for b in range(B)])
+        return self._output(logits, kv if use_cache is not False else None, labels, return_dict)
+
+    def _output(self, logits, kv, labels, return_dict):
+        loss = None
+        if labels is not None:  # HF LlamaForCausalLM loss: shift by one, ignore_index=-100
+            sl = logits[..., :-1, :].contiguous().float()
+            tl = labels[..., 1:].contiguous().to(sl.device)
+            loss = nn.functional.cross_entropy(sl.view(-1, sl.size(-1)), tl.view(-1), ignore_index=-100)
+        if return_dict is False:
+            out = (logits, kv)
+            return ((loss,) + out) if loss is not None else out
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=kv)
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        """ref llava_llama.py:101-108 (kept for API parity; generate() below does not need it)."""
+        images = kwargs.pop("images", None)
+        if past_key_values is not None:
+            input_ids = input_ids[:, -1:]
+        model_inputs = {"input_ids": input_ids, "past_key_values": past_key_values,
+                        "use_cache": kwargs.get("use_cache"), "attention_mask": kwargs.get("attention_mask")}
+        if inputs_embeds is not None and past_key_values is None:
+            model_inputs = {"inputs_embeds": inputs_embeds, **{k: v for k, v in model_inputs.items() if k != "input_ids"}}
+        if images is not None:
+            model_inputs["images"] = images
+        return model_inputs
+
+    # ------------------------------------------------------------------ generate
+    @torch.no_grad()
+    def generate(self, inputs=None, images=None, do_sample=False, temperature=1.0, top_p=None, top_k=None,
+                 num_beams=1, max_new_tokens=None, max_length=None, use_cache=True, streamer=None,
+                 stopping_criteria=None, eos_token_id=None, pad_token_id=None, attention_mask=None,
+                 input_ids=None, output_scores=False, return_dict_in_generate=False, **kwargs):
+        """Own decoding loop with the side-protocols the reference's callers rely on:
+        prompt ids (with IMAGE_TOKEN_INDEX) echoed in the result, `streamer.put/end`, `stopping_criteria`
+        called as crit(ids_so_far, scores) -> bool | bool tensor, eos stop, temperature/top-p sampling.
+        Pure greedy runs without criteria/streamer stay on the device for the whole loop (CUDA-graph replay)."""
+        if inputs is None:
+            inputs = input_ids
+        if inputs is None:
+            raise ValueError("generate() needs input ids")
+        if num_beams != 1:
+            raise NotImplementedError("beam search is not used on the LLaVA path (num_beams=1 everywhere)")
+        if return_dict_in_generate or output_scores:
+            raise NotImplementedError("generate() returns the id tensor only")
+        prompt = inputs if inputs.dim() == 2 else inputs.unsqueeze(0)
+        B, Lt = prompt.shape
+        engine = self._ensure_engine()
+        if eos_token_id is None:
+            eos_token_id = getattr(self.config, "eos_token_id", None)
+        eos_ids = set(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else ({eos_token_id} if eos_token_id is not None else set())
+        if max_new_tokens is None:
+            max_new_tokens = (max_length - Lt) if max_length is not None else 20
+        if max_new_tokens <= 0:
+            raise ValueError("max_new_tokens must be positive")
+        greedy = (not do_sample) or (temperature is not None and temperature <= 1e-5)
+
+        # ---- prefill: splice + decoder, last-position logits only ----
+        if images is not None and self.get_vision_tower() is not None:
+            _, _, _, _, embeds, _ = self.prepare_inputs_labels_for_multimodal(prompt, None, attention_mask, None, None, images)
+            lens = self._last_splice_lens
+            if getattr(self.config, "tokenizer_padding_side", "right") == "left" and len(set(lens)) > 1:
+                S = embeds.shape[1]
+                embeds = torch.stack([torch.roll(embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
+        else:
+            if attention_mask is not None and not bool(attention_mask.bool().all()):
+                raise NotImplementedError("padded text-only batches: pass equal-length prompts")
+            ids = prompt.to(torch.int32).reshape(-1).to(engine.device)
+            embeds = engine.splice(ids, None, B, Lt)
+            lens = [Lt] * B
+        S = embeds.shape[1]
+        kv = self._get_kv(B, max(lens) + max_new_tokens)
+        kv.reset()
+        logits = engine.prefill(kv, embeds, lens, LOGITS_LAST)
+
+        if streamer is not None:
+            streamer.put(prompt.cpu())
+
+        fast = greedy and streamer is None and not stopping_criteria and not eos_ids
+        if fast:
+            first = engine.argmax(logits)
+            if max_new_tokens > 1:
+                rest = engine.decode_greedy(kv, first, max_new_tokens - 1)
+                new_tokens = torch.cat([first.unsqueeze(0), rest.to(first.device)], dim=0).t()
+            else:
+                new_tokens = first.unsqueeze(1)
+            return torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
+
+        out = prompt.clone()
+        finished = torch.zeros(B, dtype=torch.bool)
+        pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
+        for step in range(max_new_tokens):
+            if greedy:
+                nxt = engine.argmax(logits)
+            else:
+                nxt = _sample(logits, temperature, top_p, top_k)
+            nxt_cpu = nxt.to("cpu", torch.long)
+            nxt_cpu = torch.where(finished, torch.full_like(nxt_cpu, pad), nxt_cpu)
+            out = torch.cat([out, nxt_cpu.to(out.device, out.dtype).unsqueeze(1)], dim=1)
+            if streamer is not None:
+                streamer.put(nxt_cpu)
+            for b in range(B):
+                if int(nxt_cpu[b]) in eos_ids:
+                    finished[b] = True
+            stop = bool(finished.all())
+            if stopping_criteria:
+                for crit in stopping_criteria:
+                    r = crit(out, None)
+                    r = bool(r.all()) if torch.is_tensor(r) else bool(r)
+                    stop = stop or r
+            if stop or step == max_new_tokens - 1:
+                break
+            logits = engine.decode_step(kv, nxt_cpu.to(torch.int32))
+        if streamer is not None:
+            streamer.end()
+        return out
+
+    # ------------------------------------------------------------------ checkpoints
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, config=None, torch_dtype=None,
+                        low_cpu_mem_usage=True, device_map=None, device=None, **kwargs):
+        """Minimal HF-style loader: `config.json` + safetensors / pytorch_model*.bin shards in a local directory
+        (ref builder.py:105-106 calls this). 8-bit/4-bit bitsandbytes loading is not part of the B200 path."""
+        if kwargs.get("load_in_8bit") or kwargs.get("load_in_4bit") or kwargs.get("quantization_config") is not None:
+            raise NotImplementedError("bitsandbytes quantised loading is not supported on the B200 path")
+        path = pretrained_model_name_or_path
+        if not os.path.isdir(path):
+            raise ValueError(f"{path!r} is not a local checkpoint directory (no network access on this path)")
+        if config is None:
+            with open(os.path.join(path, "config.json")) as f:
+                config = LlavaConfig(**json.load(f))
+        dev = device
+        if dev is None and isinstance(device_map, (str, torch.device)) and str(device_map) not in ("auto",):
+            dev = device_map
+        if dev is None:
+            dev = "cuda"
+        model = cls(config, device=dev, dtype=torch.bfloat16)
+        sd = _read_checkpoint_dir(path)
+        if not sd:
+            raise RuntimeError(f"no weight files found under {path!r}")
+        own = model.state_dict()
+        sd = {k: v for k, v in sd.items() if k in own}
+        missing = [k for k in own if k not in sd and "vision_tower" not in k]
+        if missing:
+            raise RuntimeError(f"checkpoint is missing tensors: {missing[:8]} ...")
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    def eval(self):
+        return super().eval()
+
+
+def _sample(logits, temperature, top_p, top_k):
+    """temperature / top-k / top-p sampling on last-position logits (HF LogitsWarper semantics)."""
+    x = logits.float() / max(float(temperature), 1e-5)
+    if top_k:
+        kth = torch.topk(x, int(top_k), dim=-1).values[..., -1, None]
+        x = x.masked_fill(x < kth, float("-inf"))
+    if top_p is not None and top_p < 1.0:
+        sorted_x, idx = torch.sort(x, descending=False, dim=-1)
+        cum = sorted_x.softmax(dim=-1).cumsum(dim=-1)
+        remove = cum <= (1 - top_p)
+        remove[..., -1:] = False
+        x = x.masked_fill(remove.scatter(-1, idx, remove), float("-inf"))
+    return torch.multinomial(x.softmax(dim=-1), 1).squeeze(-1).to(torch.int32)
+
+
+try:  # the installed transformers may already ship a "llava" model type (ref llava_llama.py:110-111)
+    AutoConfig.register("llava", LlavaConfig, exist_ok=True)
+except Exception:  # pragma: no cover - registry differences across transformers versions
+    pass

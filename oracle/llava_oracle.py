@@ -1,0 +1,338 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (never imported by the product path).
+
+CPU restatement, in plain PyTorch, of the reference's multimodal forward path. Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import this module.
+
+What it restates (reference = /root/reference @ a9f9d6fd; $HF = transformers 5.5.0, the version whose files
+were read; the reference pins 4.31.0 which implements the same math):
+
+  clip_vit_features     llava/model/multimodal_encoder/clip_encoder.py:29-51 (hidden_states[select_layer], drop CLS)
+                        $HF/models/clip/modeling_clip.py:202-217 (embeddings), :261-279 + :300-336 (attention),
+                        :347-351 (MLP), :363-384 (encoder layer), :667-691 (pre_layrnorm + encoder);
+                        $HF/activations.py:122-123 (quick_gelu)
+  mm_projector          llava/model/multimodal_projector/builder.py:39-46 (Linear -> GELU(erf) -> Linear)
+  encode_images         llava/model/llava_arch.py:94-97
+  prepare_multimodal    llava/model/llava_arch.py:99-240 (splice semantics, probed in SURVEY App. C)
+  llama_forward         $HF/models/llama/modeling_llama.py:62-67 (RMSNorm), :124-168 (RoPE), :182-184 (MLP),
+                        :199-221 (eager attention), :251-289 (attention module), :303-332 (decoder layer),
+                        :375-425 (model), :486-487 (lm_head); llava/model/language_model/llava_llama.py:56-99
+  greedy_generate       the manual greedy loop over the reference forward of SURVEY §8c (HF generate greedy search)
+
+Pinning: the reference ships NO tests or golden vectors for this path — "parity unpinned" by the
+reference itself. This restatement is instead pinned against OUTPUTS OF THE UNMODIFIED REFERENCE FILES run in
+the build container (tests/golden/make_golden.py -> tests/golden/*.npz; checked by tests/test_oracle_golden.py).
+
+Weights are a flat dict keyed by the reference's state-dict names. `dtype=torch.float32` is the
+parity reference; `dtype=torch.bfloat16` reproduces the rounding points of the HF bf16 path (used for the CPU
+baseline timing and for the bf16-noise tolerance).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+IGNORE_INDEX = -100
+IMAGE_TOKEN_INDEX = -200
+VT = "model.vision_tower.vision_tower.vision_model."
+
+
+# ------------------------------------------------------------------------------------------------------
+# configs + deterministic random weights (there are no checkpoints offline)
+# ------------------------------------------------------------------------------------------------------
+def make_config(hidden=4096, inter=11008, layers=32, heads=32, vocab=32000, rms_eps=1e-5, rope_theta=10000.0,
+                vit_hidden=1024, vit_inter=4096, vit_layers=24, vit_heads=16, image_size=336, patch_size=14,
+                vit_eps=1e-5, select_layer=-2):
+    return dict(hidden=hidden, inter=inter, layers=layers, heads=heads, vocab=vocab, rms_eps=rms_eps,
+                rope_theta=rope_theta, vit_hidden=vit_hidden, vit_inter=vit_inter, vit_layers=vit_layers,
+                vit_heads=vit_heads, image_size=image_size, patch_size=patch_size, vit_eps=vit_eps,
+                select_layer=select_layer)
+
+
+CONFIGS = {
+    "llava-1.5-7b": make_config(),
+    "llava-1.5-13b": make_config(hidden=5120, inter=13824, layers=40, heads=40),
+    # smallest shapes the CUDA kernels accept (head_dim 128 / 64, hidden % 256 == 0): used by the parity tests
+    "tiny": make_config(hidden=256, inter=512, layers=2, heads=2, vocab=1024, vit_hidden=256, vit_inter=512,
+                        vit_layers=3, vit_heads=4, image_size=56, patch_size=14),
+    "small": make_config(hidden=512, inter=1024, layers=3, heads=4, vocab=2048, vit_hidden=512, vit_inter=1024,
+                         vit_layers=4, vit_heads=8, image_size=112, patch_size=14),
+}
+
+
+def weight_shapes(cfg):
+    """Ordered (key, shape, kind) list; kind in {'w','b','g','emb'} drives the init."""
+    h, I, V, D, DI = cfg["hidden"], cfg["inter"], cfg["vocab"], cfg["vit_hidden"], cfg["vit_inter"]
+    T = (cfg["image_size"] // cfg["patch_size"]) ** 2 + 1
+    ps = cfg["patch_size"]
+    out = [(VT + "embeddings.class_embedding", (D,), "emb"),
+           (VT + "embeddings.patch_embedding.weight", (D, 3, ps, ps), "w"),
+           (VT + "embeddings.position_embedding.weight", (T, D), "emb"),
+           (VT + "pre_layrnorm.weight", (D,), "g"), (VT + "pre_layrnorm.bias", (D,), "b")]
+    for i in range(cfg["vit_layers"]):
+        p = VT + f"encoder.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            out += [(p + f"self_attn.{n}.weight", (D, D), "w"), (p + f"self_attn.{n}.bias", (D,), "b")]
+        out += [(p + "layer_norm1.weight", (D,), "g"), (p + "layer_norm1.bias", (D,), "b"),
+                (p + "mlp.fc1.weight", (DI, D), "w"), (p + "mlp.fc1.bias", (DI,), "b"),
+                (p + "mlp.fc2.weight", (D, DI), "w"), (p + "mlp.fc2.bias", (D,), "b"),
+                (p + "layer_norm2.weight", (D,), "g"), (p + "layer_norm2.bias", (D,), "b")]
+    out += [(VT + "post_layernorm.weight", (D,), "g"), (VT + "post_layernorm.bias", (D,), "b")]
+    out += [("model.mm_projector.0.weight", (h, D), "w"), ("model.mm_projector.0.bias", (h,), "b"),
+            ("model.mm_projector.2.weight", (h, h), "w"), ("model.mm_projector.2.bias", (h,), "b"),
+            ("model.embed_tokens.weight", (V, h), "emb")]
+    for i in range(cfg["layers"]):
+        p = f"model.layers.{i}."
+        out += [(p + "self_attn.q_proj.weight", (h, h), "w"), (p + "self_attn.k_proj.weight", (h, h), "w"),
+                (p + "self_attn.v_proj.weight", (h, h), "w"), (p + "self_attn.o_proj.weight", (h, h), "w"),
+                (p + "mlp.gate_proj.weight", (I, h), "w"), (p + "mlp.up_proj.weight", (I, h), "w"),
+                (p + "mlp.down_proj.weight", (h, I), "w"),
+                (p + "input_layernorm.weight", (h,), "g"), (p + "post_attention_layernorm.weight", (h,), "g")]
+    out += [("model.norm.weight", (h,), "g"), ("lm_head.weight", (V, h), "w")]
+    return out
+
+
+def init_std(kind, shape):
+    """Synthetic init: unit-gain linears (so activations stay O(1) through depth and logits have a healthy
+    spread for argmax tests), norm gains around 1, small non-zero biases so every fused-bias path is exercised."""
+    if kind == "w":
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return 1.0 / math.sqrt(fan_in)
+    if kind == "emb":
+        return 1.0 if len(shape) == 2 else 0.5
+    if kind == "b":
+        return 0.05
+    return 0.1  # 'g': 1 + 0.1*N
+
+
+def make_weights(cfg, seed=0, dtype=torch.float32):
+    """Deterministic CPU weights (values rounded through bf16 so fp32 oracle and bf16 engine see identical numbers)."""
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    for key, shape, kind in weight_shapes(cfg):
+        t = torch.randn(*shape, generator=g) * init_std(kind, shape)
+        if kind == "g":
+            t = t + 1.0
+        w[key] = t.to(torch.bfloat16).to(dtype)
+    return w
+
+
+# ------------------------------------------------------------------------------------------------------
+# CLIP ViT + projector
+# ------------------------------------------------------------------------------------------------------
+def _quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def clip_vit_features(w, pixels, cfg, dtype=torch.float32):
+    """pixels [B,3,H,W] -> hidden_states[select_layer][:, 1:]  ([B, P, D])."""
+    D, H = cfg["vit_hidden"], cfg["vit_heads"]
+    d = D // H
+    ps, eps = cfg["patch_size"], cfg["vit_eps"]
+    x = pixels.to(dtype)
+    B = x.shape[0]
+    W = lambda k: w[VT + k].to(dtype)
+    patches = F.conv2d(x, W("embeddings.patch_embedding.weight"), stride=ps).flatten(2).transpose(1, 2)
+    cls = W("embeddings.class_embedding").expand(B, 1, -1)
+    hcur = torch.cat([cls, patches], dim=1) + W("embeddings.position_embedding.weight")
+    hcur = F.layer_norm(hcur, (D,), W("pre_layrnorm.weight"), W("pre_layrnorm.bias"), eps)
+    n_layers = cfg["vit_layers"]
+    sel = cfg["select_layer"]
+    live = n_layers + 1 + sel if sel < 0 else sel  # hidden_states[live] == output of layer `live` (0 = embeddings)
+    for i in range(live):
+        p = f"encoder.layers.{i}."
+        res = hcur
+        y = F.layer_norm(hcur, (D,), W(p + "layer_norm1.weight"), W(p + "layer_norm1.bias"), eps)
+        T = y.shape[1]
+        q = F.linear(y, W(p + "self_attn.q_proj.weight"), W(p + "self_attn.q_proj.bias")).view(B, T, H, d).transpose(1, 2)
+        k = F.linear(y, W(p + "self_attn.k_proj.weight"), W(p + "self_attn.k_proj.bias")).view(B, T, H, d).transpose(1, 2)
+        v = F.linear(y, W(p + "self_attn.v_proj.weight"), W(p + "self_attn.v_proj.bias")).view(B, T, H, d).transpose(1, 2)
+        att = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
+        att = torch.softmax(att, dim=-1, dtype=torch.float32).to(dtype)
+        y = torch.matmul(att, v).transpose(1, 2).reshape(B, T, D)
+        y = F.linear(y, W(p + "self_attn.out_proj.weight"), W(p + "self_attn.out_proj.bias"))
+        hcur = res + y
+        res = hcur
+        y = F.layer_norm(hcur, (D,), W(p + "layer_norm2.weight"), W(p + "layer_norm2.bias"), eps)
+        y = _quick_gelu(F.linear(y, W(p + "mlp.fc1.weight"), W(p + "mlp.fc1.bias")))
+        y = F.linear(y, W(p + "mlp.fc2.weight"), W(p + "mlp.fc2.bias"))
+        hcur = res + y
+    return hcur[:, 1:]
+
+
+def mm_projector(w, feats, dtype=torch.float32):
+    x = feats.to(dtype)
+    x = F.linear(x, w["model.mm_projector.0.weight"].to(dtype), w["model.mm_projector.0.bias"].to(dtype))
+    x = F.gelu(x)  # exact erf GELU (nn.GELU default)
+    return F.linear(x, w["model.mm_projector.2.weight"].to(dtype), w["model.mm_projector.2.bias"].to(dtype))
+
+
+def encode_images(w, pixels, cfg, dtype=torch.float32):
+    return mm_projector(w, clip_vit_features(w, pixels, cfg, dtype), dtype)
+
+
+# ------------------------------------------------------------------------------------------------------
+# splice (prepare_inputs_labels_for_multimodal, prefill branch)
+# ------------------------------------------------------------------------------------------------------
+def prepare_multimodal(w, input_ids, images, cfg, attention_mask=None, labels=None, padding_side="right",
+                       max_length=None, dtype=torch.float32, image_features=None):
+    """Returns (inputs_embeds [B,S,h], attention_mask bool [B,S], position_ids [B,S], labels [B,S]).
+
+    `images`: [n,3,H,W], or a list / 5-D tensor of per-row image groups (each group flattened into one
+    <image> slot). The k-th image slot is consumed by the k-th IMAGE_TOKEN_INDEX in row-major order; a row
+    without any still consumes one slot (llava_arch.py:149-181)."""
+    emb = w["model.embed_tokens.weight"].to(dtype)
+    if image_features is None:
+        if isinstance(images, (list, tuple)) or images.dim() == 5:
+            groups = [g for g in images]
+            feats = encode_images(w, torch.cat(groups, dim=0), cfg, dtype)
+            image_features, o = [], 0
+            for grp in groups:
+                image_features.append(feats[o:o + grp.shape[0]].flatten(0, 1))
+                o += grp.shape[0]
+        else:
+            image_features = list(encode_images(w, images, cfg, dtype))
+    B = input_ids.shape[0]
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids, dtype=torch.bool)
+    attention_mask = attention_mask.bool()
+    if labels is None:
+        labels = torch.full_like(input_ids, IGNORE_INDEX)
+    rows_e, rows_l = [], []
+    slot = 0
+    for b in range(B):
+        ids = input_ids[b][attention_mask[b]]
+        lab = labels[b][attention_mask[b]]
+        where = (ids == IMAGE_TOKEN_INDEX).nonzero().flatten().tolist()
+        if not where:
+            _ = image_features[slot]  # consumes a slot, contributes zero rows
+            slot += 1
+            rows_e.append(emb[ids])
+            rows_l.append(lab)
+            continue
+        pe, pl, prev = [], [], -1
+        for p in where + [ids.shape[0]]:
+            seg = ids[prev + 1:p]
+            pe.append(emb[seg])
+            pl.append(lab[prev + 1:p])
+            if p < ids.shape[0]:
+                f = image_features[slot]
+                slot += 1
+                pe.append(f)
+                pl.append(torch.full((f.shape[0],), IGNORE_INDEX, dtype=lab.dtype))
+            prev = p
+        rows_e.append(torch.cat(pe))
+        rows_l.append(torch.cat(pl))
+    if max_length is not None:
+        rows_e = [r[:max_length] for r in rows_e]
+        rows_l = [r[:max_length] for r in rows_l]
+    S = max(r.shape[0] for r in rows_e)
+    h = emb.shape[1]
+    embeds = torch.zeros(B, S, h, dtype=dtype)
+    new_labels = torch.full((B, S), IGNORE_INDEX, dtype=labels.dtype)
+    mask = torch.zeros(B, S, dtype=torch.bool)
+    pos = torch.zeros(B, S, dtype=torch.long)
+    for b in range(B):
+        n = rows_e[b].shape[0]
+        if n == 0:
+            continue
+        sl = slice(S - n, S) if padding_side == "left" else slice(0, n)
+        embeds[b, sl] = rows_e[b]
+        new_labels[b, sl] = rows_l[b]
+        mask[b, sl] = True
+        pos[b, sl] = torch.arange(n)
+    return embeds, mask, pos, new_labels
+
+
+# ------------------------------------------------------------------------------------------------------
+# LLaMA decoder
+# ------------------------------------------------------------------------------------------------------
+def _rmsnorm(x, weight, eps):
+    dt = x.dtype
+    xf = x.float()
+    xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return weight * xf.to(dt)
+
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def _rope_cos_sin(position_ids, d, theta, dtype):
+    inv_freq = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    freqs = position_ids[:, :, None].float() * inv_freq[None, None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def llama_forward(w, inputs_embeds, cfg, position_ids=None, attention_mask=None, kv=None, dtype=torch.float32,
+                  last_only=False):
+    """inputs_embeds [B,S,h]; kv: list of (k,v) [B,H,L,d] per layer or None. Returns (logits fp32, new kv).
+
+    attention_mask: bool [B, L+S] over cached+new positions (None = all valid)."""
+    h, H = cfg["hidden"], cfg["heads"]
+    d = h // H
+    x = inputs_embeds.to(dtype)
+    B, S, _ = x.shape
+    past = 0 if kv is None else kv[0][0].shape[2]
+    if position_ids is None:
+        position_ids = torch.arange(past, past + S)[None, :].expand(B, S)
+    cos, sin = _rope_cos_sin(position_ids, d, cfg["rope_theta"], dtype)
+    cos, sin = cos[:, None], sin[:, None]
+    L = past + S
+    causal = torch.full((S, L), float("-inf"))
+    causal = torch.triu(causal, diagonal=past + 1)
+    mask = causal[None, None].expand(B, 1, S, L).clone()
+    if attention_mask is not None:
+        mask = mask.masked_fill(~attention_mask.bool()[:, None, None, :], float("-inf"))
+    mask = mask.to(dtype)
+    new_kv = []
+    for i in range(cfg["layers"]):
+        p = f"model.layers.{i}."
+        W = lambda k: w[p + k].to(dtype)
+        res = x
+        y = _rmsnorm(x, W("input_layernorm.weight"), cfg["rms_eps"])
+        q = F.linear(y, W("self_attn.q_proj.weight")).view(B, S, H, d).transpose(1, 2)
+        k = F.linear(y, W("self_attn.k_proj.weight")).view(B, S, H, d).transpose(1, 2)
+        v = F.linear(y, W("self_attn.v_proj.weight")).view(B, S, H, d).transpose(1, 2)
+        q = q * cos + _rotate_half(q) * sin
+        k = k * cos + _rotate_half(k) * sin
+        if kv is not None:
+            k = torch.cat([kv[i][0], k], dim=2)
+            v = torch.cat([kv[i][1], v], dim=2)
+        new_kv.append((k, v))
+        att = torch.matmul(q, k.transpose(2, 3)) * (d ** -0.5) + mask
+        att = torch.softmax(att, dim=-1, dtype=torch.float32).to(dtype)
+        y = torch.matmul(att, v).transpose(1, 2).reshape(B, S, h)
+        x = res + F.linear(y, W("self_attn.o_proj.weight"))
+        res = x
+        y = _rmsnorm(x, W("post_attention_layernorm.weight"), cfg["rms_eps"])
+        y = F.linear(F.silu(F.linear(y, W("mlp.gate_proj.weight"))) * F.linear(y, W("mlp.up_proj.weight")),
+                     W("mlp.down_proj.weight"))
+        x = res + y
+    x = _rmsnorm(x, w["model.norm.weight"].to(dtype), cfg["rms_eps"])
+    if last_only:
+        x = x[:, -1:]
+    logits = F.linear(x, w["lm_head.weight"].to(dtype))
+    return logits.float(), new_kv
+
+
+def greedy_generate(w, input_ids, images, cfg, max_new_tokens, dtype=torch.float32, return_logits=False):
+    """Equal-length prompts (the reference never batches generation, model_vqa_loader.py:66). Returns new token
+    ids [B, N] (and the per-step last-position logits [N, B, V])."""
+    embeds, mask, pos, _ = prepare_multimodal(w, input_ids, images, cfg, dtype=dtype)
+    logits, kv = llama_forward(w, embeds, cfg, dtype=dtype, last_only=True)
+    toks, steps = [], []
+    for _ in range(max_new_tokens):
+        last = logits[:, -1]
+        steps.append(last)
+        nxt = last.argmax(-1)
+        toks.append(nxt)
+        if len(toks) == max_new_tokens:
+            break
+        e = w["model.embed_tokens.weight"].to(dtype)[nxt][:, None]
+        logits, kv = llama_forward(w, e, cfg, kv=kv, dtype=dtype, last_only=True)
+    out = torch.stack(toks, dim=1)
+    return (out, torch.stack(steps)) if return_logits else out
