@@ -97,6 +97,10 @@ struct b2_kv {
     // cached decode-step graph
     cudaGraphExec_t graph = nullptr;
     int graph_B = 0;
+    // stream capture is illegal on the legacy default stream (torch's default current stream): decode steps
+    // run on this library-owned stream, ordered against the caller's stream with events
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int warm_B = 0;  // an eager step has run for this B (function attributes set, driver entry points resolved)
     size_t layer_stride() const { return (size_t)max_batch * m->d.heads * max_seq * m->hd; }
 };
@@ -389,6 +393,26 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     return 0;
 }
 
+// caller stream -> stream the decode steps run on (fork), and back (join)
+int fork_stream(b2_kv* kv, cudaStream_t st, cudaStream_t* run) {
+    if (st != nullptr && st != cudaStreamLegacy) { *run = st; return 0; }
+    if (kv->own_stream == nullptr) {
+        B2_CUDA_CHECK(cudaStreamCreateWithFlags(&kv->own_stream, cudaStreamNonBlocking));
+        B2_CUDA_CHECK(cudaEventCreateWithFlags(&kv->ev_fork, cudaEventDisableTiming));
+        B2_CUDA_CHECK(cudaEventCreateWithFlags(&kv->ev_join, cudaEventDisableTiming));
+    }
+    B2_CUDA_CHECK(cudaEventRecord(kv->ev_fork, st));
+    B2_CUDA_CHECK(cudaStreamWaitEvent(kv->own_stream, kv->ev_fork, 0));
+    *run = kv->own_stream;
+    return 0;
+}
+int join_stream(b2_kv* kv, cudaStream_t st, cudaStream_t run) {
+    if (run == st) return 0;
+    B2_CUDA_CHECK(cudaEventRecord(kv->ev_join, run));
+    B2_CUDA_CHECK(cudaStreamWaitEvent(st, kv->ev_join, 0));
+    return 0;
+}
+
 // run one step, through the cached CUDA graph when possible
 int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     if (kv->warm_B != B) {
@@ -671,6 +695,9 @@ int b2_kv_destroy(b2_kv* kv) {
     cudaSetDevice(kv->m->device);
     cudaDeviceSynchronize();
     if (kv->graph) cudaGraphExecDestroy(kv->graph);
+    if (kv->own_stream) cudaStreamDestroy(kv->own_stream);
+    if (kv->ev_fork) cudaEventDestroy(kv->ev_fork);
+    if (kv->ev_join) cudaEventDestroy(kv->ev_join);
     DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
                     &kv->attn_counters};
     for (DevBuf* b : bs) b->free();
@@ -815,7 +842,10 @@ int b2_decode_step(b2_model* m, b2_kv* kv, const int32_t* tokens, int B, void* l
                      kv->max_seq);
     B2_TRY(copy_tokens_in(kv, tokens, B, st));
     B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
-    B2_TRY(decode_step_run(m, kv, B, st));
+    cudaStream_t run = nullptr;
+    B2_TRY(fork_stream(kv, st, &run));
+    B2_TRY(decode_step_run(m, kv, B, run));
+    B2_TRY(join_stream(kv, st, run));
     for (int b = 0; b < B; ++b) kv->len_host[b]++;
     if (logits_out)
         B2_CUDA_CHECK(cudaMemcpyAsync(logits_out, m->logits.p, (size_t)B * m->d.vocab * 4, cudaMemcpyDefault, st));
@@ -842,7 +872,10 @@ int b2_decode_greedy(b2_model* m, b2_kv* kv, const int32_t* first_tokens, int B,
                      n_steps, kv->max_seq);
     B2_TRY(copy_tokens_in(kv, first_tokens, B, st));
     B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
-    for (int s = 0; s < n_steps; ++s) B2_TRY(decode_step_run(m, kv, B, st));
+    cudaStream_t run = nullptr;
+    B2_TRY(fork_stream(kv, st, &run));
+    for (int s = 0; s < n_steps; ++s) B2_TRY(decode_step_run(m, kv, B, run));
+    B2_TRY(join_stream(kv, st, run));
     for (int b = 0; b < B; ++b) kv->len_host[b] += n_steps;
     B2_CUDA_CHECK(cudaMemcpyAsync(out_tokens, kv->out_tokens.p, (size_t)n_steps * B * 4, cudaMemcpyDefault, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
