@@ -1,0 +1,398 @@
+"""bench.py — LLaVA-1.5 multimodal forward path on B200 (BASELINE.json metric: prefill+decode tokens/s).
+
+  python bench.py [--gpus N --steps K --warmup W]            our sm_100a path (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                     the reference's CPU path (oracle port) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input: encode_images (CLIP ViT-L/14-336 +
+mlp2x_gelu) -> splice -> LLaMA prefill over 576 image tokens + 128 text tokens -> 256 greedy decode tokens,
+i.e. BASELINE.json configs[1] (LLaVA-1.5-7B bf16, 336 px, bs=1 per GPU). Random-init weights of that
+architecture and synthetic inputs (no network for checkpoints/datasets).
+
+value   : tokens/s = n_gpus * B * (S_prefill + N_decode) / (max-over-ranks device time per step), inputs resident
+          in HBM, CUDA events on the launching stream.
+e2e     : same metric through the public API model.generate(input_ids, images=...) with HOST (pinned) inputs:
+          H2D of pixels + ids and D2H of the generated ids inside the timed region.
+roofline: the decode step (one CUDA-graph launch: weight-streaming GEMV kernels + split-KV attention for all
+          layers + lm_head), HBM-bound: algorithmic bytes/step = W + B*(Lc+1)*kv over the measured
+          step time, against MEASURED_PEAKS.json hbm_gbs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "llava-plus-codebase_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+
+import torch  # noqa: E402
+
+MODELS = {
+    "7b": dict(name="LLaVA-1.5-7B", hidden=4096, inter=11008, layers=32, heads=32),
+    "13b": dict(name="LLaVA-1.5-13B", hidden=5120, inter=13824, layers=40, heads=40),
+}
+VOCAB, P_IMG, VIT_GF, IMAGE_TOKEN = 32000, 576, 366.03, -200
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="7b", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=1, help="samples per GPU")
+    ap.add_argument("--prompt", type=int, default=128, help="text tokens (one <image> placeholder is added)")
+    ap.add_argument("--new", type=int, default=256, help="greedy decode tokens")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return float(pk["hbm_gbs"]), float(pk["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def algorithmic_work(m, B, S, N):
+    h, I, L = m["hidden"], m["inter"], m["layers"]
+    layer_params = 4 * h * h + 3 * h * I
+    w_bytes = 2 * (L * (layer_params + 2 * h) + h + VOCAB * h)     # decode weight stream (bf16), SURVEY §8d
+    kv_per_tok = 2 * 2 * h * L                                     # K+V bf16, all layers, per token per sample
+    prefill_flops = B * (2 * S * layer_params * L + 2 * S * S * h * L + 2 * h * VOCAB)
+    encode_flops = B * (VIT_GF * 1e9 + 2 * P_IMG * (1024 * h + h * h))
+    # decode step j (j = 0..N-2) runs against Lc = S + j cached tokens
+    steps = max(N - 1, 1)
+    avg_lc = S + (steps - 1) / 2.0
+    decode_bytes_per_step = w_bytes + B * (avg_lc + 1) * kv_per_tok
+    return dict(w_bytes=w_bytes, kv_per_tok=kv_per_tok, prefill_flops=prefill_flops, encode_flops=encode_flops,
+                decode_bytes_per_step=decode_bytes_per_step)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference CPU path (oracle port) — bounded sample, extrapolated
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=torch.bfloat16):
+    """Times the reference's algorithm (oracle/llava_oracle.py, HF-bf16 rounding points) on the host cores at
+    the full LLaVA dims on a bounded sample: ViT+projector in full, `sample_layers` of the decoder layers for a
+    full S-token prefill and `decode_steps` decode steps, lm_head measured separately; the per-layer time is
+    extrapolated to all layers (layer cost is uniform). Returns tokens/s for the whole step + the breakdown."""
+    from oracle import llava_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.make_config(hidden=m["hidden"], inter=m["inter"], layers=sample_layers, heads=m["heads"])
+    g = torch.Generator().manual_seed(0)
+    w = {}
+    for key, shape, kind in O.weight_shapes(cfg):
+        t = torch.empty(*shape, dtype=dtype).normal_(0.0, O.init_std(kind, shape), generator=g)
+        w[key] = t + 1.0 if kind == "g" else t
+    images = torch.randn(1, 3, 336, 336, generator=g)
+    ids = torch.randint(3, VOCAB, (1, S - P_IMG + 1), generator=g)
+    ids[0, 5] = IMAGE_TOKEN
+    cfg0 = dict(cfg, layers=0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        feats = O.encode_images(w, images, cfg, dtype=dtype)
+        t_enc = time.perf_counter() - t0
+        embeds, _, _, _ = O.prepare_multimodal(w, ids, None, cfg, dtype=dtype, image_features=list(feats))
+        O.llama_forward(w, embeds[:, :64], cfg, dtype=dtype)  # warm-up (thread pool, allocator)
+        t0 = time.perf_counter()
+        _, kv = O.llama_forward(w, embeds, cfg, dtype=dtype)          # the reference runs lm_head on all S positions
+        t_pre_L = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.llama_forward(w, embeds, cfg0, dtype=dtype)
+        t_pre_0 = time.perf_counter() - t0
+        e = embeds[:, -1:]
+        t_dec_L = 0.0
+        for _ in range(decode_steps):
+            t0 = time.perf_counter()
+            _, kv = O.llama_forward(w, e, cfg, kv=kv, dtype=dtype)
+            t_dec_L += time.perf_counter() - t0
+        t_dec_L /= decode_steps
+        t0 = time.perf_counter()
+        for _ in range(decode_steps):
+            O.llama_forward(w, e, cfg0, dtype=dtype)
+        t_dec_0 = (time.perf_counter() - t0) / decode_steps
+    L = m["layers"]
+    per_layer_pre = max(t_pre_L - t_pre_0, 0.0) / sample_layers
+    per_layer_dec = max(t_dec_L - t_dec_0, 0.0) / sample_layers
+    t_prefill = t_pre_0 + per_layer_pre * L
+    t_decode_step = t_dec_0 + per_layer_dec * L
+    total = t_enc + t_prefill + (N - 1) * t_decode_step
+    return dict(value=(S + N) / total, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
+                sample=(f"oracle port (bf16, HF rounding points) at full {m['name']} dims: ViT+projector 1 image in full, "
+                        f"{sample_layers} of {L} decoder layers for an S={S} prefill (lm_head on all positions, as the "
+                        f"reference does) and {decode_steps} decode steps, per-layer time extrapolated x{L}/{sample_layers}"),
+                breakdown=dict(encode_s=t_enc, prefill_s=t_prefill, decode_step_s=t_decode_step,
+                               prefill_tok_s=S / t_prefill, decode_tok_s=1.0 / t_decode_step),
+                measured_s=t_enc + t_pre_L + t_pre_0 + decode_steps * (t_dec_L + t_dec_0))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    m = MODELS[args.model]
+    S = P_IMG + args.prompt
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_sample(m, S, args.new, sample_layers=2 if i < args.warmup else 4,
+                                    decode_steps=2 if i < args.warmup else 4)
+        if i >= args.warmup:
+            vals.append(last)
+    value = sum(v["value"] for v in vals) / len(vals)
+    total_s = (S + args.new) / value
+    out = {
+        "impl": "reference", "metric": "prefill+decode tokens/s", "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, m, S),
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": last["cores"], "kind": "port",
+                         "sample": last["sample"], "breakdown": last["breakdown"]},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(args, m, S):
+    return {"workload": f"{m['name']} bf16, one 336px image/sample, bs={args.batch}/GPU: {P_IMG} image tokens + "
+                        f"{args.prompt} text prefill (S={S}), {args.new}-token greedy decode (BASELINE.json configs[1])",
+            "global_batch": args.batch * args.gpus, "seq_len": S, "new_tokens": args.new, "parallelism": f"dp{args.gpus} replicas",
+            "l2": "working set (13.5 GB weights streamed every decode step) >> 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our path
+# ---------------------------------------------------------------------------------------------------------
+def build_model(m, device, max_batch, max_seq):
+    from helpers import write_clip_config_dir, make_llava_config
+    from llava.model import LlavaLlamaForCausalLM
+    from oracle.llava_oracle import make_config, weight_shapes, init_std  # shapes/init table only (no compute)
+
+    cfg = make_config(hidden=m["hidden"], inter=m["inter"], layers=m["layers"], heads=m["heads"])
+    clip_dir = write_clip_config_dir(cfg)
+    model = LlavaLlamaForCausalLM(make_llava_config(cfg, clip_dir), device=device, max_batch=max_batch,
+                                  max_seq=max_seq, max_images=min(max_batch, 16))
+    model.get_vision_tower().load_model(random_init=True)
+    model.to(device=device, dtype=torch.bfloat16)
+    gen = torch.Generator(device=device).manual_seed(0)
+    sd = model.state_dict()
+    kinds = {k: (shape, kind) for k, shape, kind in weight_shapes(cfg)}
+    with torch.no_grad():
+        for k, p in sd.items():
+            shape, kind = kinds[k]
+            p.normal_(0.0, init_std(kind, shape), generator=gen)
+            if kind == "g":
+                p.add_(1.0)
+    model.invalidate_engine()
+    return model.eval()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from llava import _b2
+    from llava._b2 import replicas
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    m = MODELS[args.model]
+    B, N = args.batch, args.new
+    Lt = args.prompt + 1
+    S = args.prompt + P_IMG
+    model = build_model(m, dev, B, S + N + 8)
+    engine = model._ensure_engine()
+
+    g = torch.Generator().manual_seed(1 + rank)
+    images_host = torch.randn(B, 3, 336, 336, generator=g).pin_memory()
+    ids_host = torch.randint(3, VOCAB, (B, Lt), generator=g)
+    ids_host[:, 0] = 1
+    ids_host[:, 5] = IMAGE_TOKEN
+    ids_host = ids_host.pin_memory()
+
+    stream = torch.cuda.Stream(device=dev)
+    work = algorithmic_work(m, B, S, N)
+    hbm_peak, tf_peak, peak_kind = peaks()
+
+    with torch.cuda.stream(stream), torch.no_grad():
+        # ---------------- device-resident arm ----------------
+        pixels = images_host.to(dev, torch.bfloat16)
+        from llava.model.llava_arch import build_source_index
+        import numpy as np
+        ids_np = ids_host.numpy().astype(np.int64)
+        src, _, _, _, lens = build_source_index(ids_np, np.ones_like(ids_np, bool), np.full_like(ids_np, -100),
+                                                B * P_IMG, [P_IMG] * B, None, "right")
+        src_dev = torch.from_numpy(src.reshape(-1)).to(dev)
+        kv = engine.new_kv(B, S + N + 8)
+        out_tokens = torch.empty(max(N - 1, 1), B, dtype=torch.int32, device=dev)
+
+        def device_step(ev=None):
+            if ev: ev[0].record()
+            feats = engine.encode_images(pixels)
+            if ev: ev[1].record()
+            embeds = engine.splice(src_dev, feats.view(-1, feats.shape[-1]), B, S)
+            kv.reset()
+            logits = engine.prefill(kv, embeds, lens, _b2.LOGITS_LAST)
+            first = engine.argmax(logits)
+            if ev: ev[2].record()
+            if N > 1:
+                engine.decode_greedy(kv, first, N - 1, out=out_tokens)
+            if ev: ev[3].record()
+            return first
+
+        for _ in range(args.warmup):
+            device_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        launches0 = _b2.launch_count()
+        for i in range(args.steps):
+            device_step(evs[i])
+        torch.cuda.synchronize()
+        launches = _b2.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        t_enc = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+        t_pre = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+        t_dec = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+        t_total = evs[0][0].elapsed_time(evs[-1][3]) / args.steps  # ms per step, back to back
+        t_total = replicas.max_over_ranks(t_total, dev)
+        t_enc_m, t_pre_m, t_dec_m = (replicas.max_over_ranks(t, dev) for t in (t_enc, t_pre, t_dec))
+        tokens_per_step = world * B * (S + N)
+        value = tokens_per_step / (t_total * 1e-3)
+
+        # ---------------- end-to-end arm: public API, host buffers ----------------
+        e2e = None
+        if not args.no_e2e:
+            def api_step():
+                return model.generate(ids_host, images=images_host, do_sample=False, max_new_tokens=N, use_cache=True)
+            for _ in range(max(1, min(args.warmup, 2))):
+                api_step()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                out = api_step()
+            e1.record()
+            torch.cuda.synchronize()
+            assert out.shape == (B, Lt + N) and out.device.type == "cpu"
+            t_e2e = replicas.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+            e2e = {"value": tokens_per_step / (t_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": t_e2e,
+                   "h2d_bytes_per_step": int(images_host.numel() * 4 + ids_host.numel() * 8 + B * S * 4),
+                   "d2h_bytes_per_step": int(B * N * 4)}
+        # eval-harness gather of the generated ids over NCCL (outside the timed region; never on the hot path)
+        if world > 1:
+            replicas.gather_rows(out_tokens.t().contiguous(), world * B)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    steps_dec = max(N - 1, 1)
+    dec_step_ms = t_dec_m / steps_dec
+    achieved = work["decode_bytes_per_step"] / (dec_step_ms * 1e-3) / 1e9
+    out = {
+        "metric": "prefill+decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, m, S),
+        "breakdown": {"encode_images_ms": t_enc_m, "prefill_ms": t_pre_m, "decode_ms": t_dec_m,
+                      "decode_ms_per_token": dec_step_ms, "images_per_s": world * B / (t_enc_m * 1e-3),
+                      "prefill_tok_s": world * B * S / (t_pre_m * 1e-3),
+                      "decode_tok_s": world * B * steps_dec / (t_dec_m * 1e-3),
+                      "prefill_tflops": work["prefill_flops"] / (t_pre_m * 1e-3) / 1e12,
+                      "prefill_frac_of_bf16_peak": work["prefill_flops"] / (t_pre_m * 1e-3) / 1e12 / tf_peak,
+                      "encode_tflops": work["encode_flops"] / (t_enc_m * 1e-3) / 1e12},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                     "kernel": "decode step = one CUDA-graph launch (gemv_kernel x4 + decode_attn_kernel per layer, "
+                               "lm_head gemv, argmax)",
+                     "algorithmic_bytes_per_launch": work["decode_bytes_per_step"],
+                     "avg_launch_ms": dec_step_ms},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_reference_sample(m, S, N)
+        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "breakdown")}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py (our arm) needs a B200; there is no CPU fallback. Use --impl reference for the CPU arm.")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
