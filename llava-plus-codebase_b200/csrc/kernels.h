@@ -1,6 +1,7 @@
 // Internal launcher declarations for the b2llava kernels (C++ side, not part of the C ABI).
 // All tensors are device pointers; activations/weights are bf16 unless stated otherwise.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -89,6 +90,26 @@ struct DecodeAttnArgs {
     float theta = 10000.f, scale = 1.f;
 };
 int decode_attn_bf16(const DecodeAttnArgs& a, cudaStream_t stream);
+
+// ---- persistent decode-step megakernel (decode_mega.cu), batch <= 8 ------------------------------------
+struct MegaLayer {
+    const __nv_bfloat16 *ln1, *wqkv, *wo, *ln2, *wgu, *wd;
+    __nv_bfloat16 *kcache, *vcache;  // this layer's [Bmax, H, Smax, 128] slabs
+};
+struct MegaParams {
+    const MegaLayer* layers = nullptr;  // device array [L]
+    int L = 0, h = 0, I = 0, H = 0, V = 0, B = 0, Smax = 0, nsplit = 1;
+    const __nv_bfloat16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+    int32_t *tok = nullptr, *cur_len = nullptr, *out_tokens = nullptr, *step_counter = nullptr;
+    __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr;
+    float* logits = nullptr;
+    float* attn_partial = nullptr;      // [B*H*nsplit*(128+2)]
+    int32_t* attn_counters = nullptr;   // [B*H], zero-initialised, self-resetting
+    unsigned int *bar_count = nullptr, *bar_gen = nullptr, *done_count = nullptr;  // zero-initialised
+    float eps = 1e-5f, theta = 10000.f, scale_log2 = 1.f;
+};
+// one launch = embed -> all layers -> lm_head -> argmax -> token store; cur_len/step_counter advance on device
+int decode_mega(const MegaParams& p, cudaStream_t stream);
 
 // ---- misc (misc_ops.cu) ----------------------------------------------------------------------------
 // out[r, :] = src_index[r] >= 0 ? table[src_index[r]] : (src_index[r] == INT32_MIN ? 0 : feats[-src_index[r]-1])

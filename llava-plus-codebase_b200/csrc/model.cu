@@ -5,6 +5,7 @@
 #include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -99,6 +100,7 @@ struct b2_kv {
     int graph_B = 0;
     // stream capture is illegal on the legacy default stream (torch's default current stream): decode steps
     // run on this library-owned stream, ordered against the caller's stream with events
+    DevBuf mega_layers, mega_sync;  // MegaLayer[L] table and {bar_count, bar_gen, done_count}
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int warm_B = 0;  // an eager step has run for this B (function attributes set, driver entry points resolved)
@@ -414,7 +416,38 @@ int join_stream(b2_kv* kv, cudaStream_t st, cudaStream_t run) {
 }
 
 // run one step, through the cached CUDA graph when possible
+bool use_mega(int B) {
+    static int flag = -1;
+    if (flag < 0) {
+        const char* e = getenv("B2_DECODE_MEGA");
+        flag = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return flag == 1 && B <= 8;
+}
+
+int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
+    const b2_model_desc& d = m->d;
+    MegaParams p;
+    p.layers = kv->mega_layers.as<MegaLayer>();
+    p.L = d.layers; p.h = d.hidden; p.I = d.inter; p.H = d.heads; p.V = d.vocab; p.B = B; p.Smax = kv->max_seq;
+    int ns = (num_sms() * 16) / (B * d.heads);
+    p.nsplit = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
+    p.embed = m->embed.as<bf16>(); p.final_norm = m->final_norm.as<bf16>(); p.lm_head = m->lm_head.as<bf16>();
+    p.tok = kv->tok.as<int32_t>(); p.cur_len = kv->len_dev.as<int32_t>();
+    p.out_tokens = kv->out_tokens.as<int32_t>(); p.step_counter = kv->step_counter.as<int32_t>();
+    p.x = m->x.as<bf16>(); p.qkv = m->qkv.as<bf16>(); p.attn = m->attn.as<bf16>(); p.act = m->act.as<bf16>();
+    p.logits = m->logits.as<float>();
+    p.attn_partial = kv->attn_partial.as<float>(); p.attn_counters = kv->attn_counters.as<int32_t>();
+    unsigned int* sync = kv->mega_sync.as<unsigned int>();
+    p.bar_count = sync; p.bar_gen = sync + 1; p.done_count = sync + 2;
+    p.eps = d.rms_eps; p.theta = d.rope_theta;
+    p.scale_log2 = (1.0f / sqrtf((float)m->hd)) * 1.4426950408889634f;
+    return decode_mega(p, st);
+}
+
 int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
+    // B <= 8: one persistent cooperative launch per token (no graph needed: launches queue asynchronously)
+    if (use_mega(B)) return decode_step_mega(m, kv, B, st);
     if (kv->warm_B != B) {
         // first step for this batch size runs eagerly: sets function attributes, resolves driver entry points
         if (kv->graph) { cudaGraphExecDestroy(kv->graph); kv->graph = nullptr; kv->graph_B = 0; }
@@ -662,7 +695,23 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
         return r;
     }
     kv->out_capacity = max_seq;
-    const int max_split = 32;
+    const int max_split = 64;
+    {
+        std::vector<MegaLayer> tbl(m->d.layers);
+        for (int l = 0; l < m->d.layers; ++l) {
+            LlamaLayer& L = m->ll[l];
+            tbl[l].ln1 = L.ln1.as<bf16>(); tbl[l].wqkv = L.wqkv.as<bf16>(); tbl[l].wo = L.wo.as<bf16>();
+            tbl[l].ln2 = L.ln2.as<bf16>(); tbl[l].wgu = L.wgu.as<bf16>(); tbl[l].wd = L.wd.as<bf16>();
+            tbl[l].kcache = kv->k.as<bf16>() + (size_t)l * kv->layer_stride();
+            tbl[l].vcache = kv->v.as<bf16>() + (size_t)l * kv->layer_stride();
+        }
+        if ((r = kv->mega_layers.alloc(tbl.size() * sizeof(MegaLayer))) != 0 || (r = kv->mega_sync.alloc(64)) != 0) {
+            b2_kv_destroy(kv);
+            return r;
+        }
+        cudaMemcpy(kv->mega_layers.p, tbl.data(), tbl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice);
+        cudaMemset(kv->mega_sync.p, 0, 64);
+    }
     if ((r = kv->out_tokens.alloc((size_t)kv->out_capacity * max_batch * 4)) != 0 ||
         (r = kv->attn_partial.alloc((size_t)max_batch * m->d.heads * max_split * (128 + 2) * 4)) != 0 ||
         (r = kv->attn_counters.alloc((size_t)max_batch * m->d.heads * 4)) != 0) {
@@ -699,7 +748,7 @@ int b2_kv_destroy(b2_kv* kv) {
     if (kv->ev_fork) cudaEventDestroy(kv->ev_fork);
     if (kv->ev_join) cudaEventDestroy(kv->ev_join);
     DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
-                    &kv->attn_counters};
+                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync};
     for (DevBuf* b : bs) b->free();
     delete kv;
     return 0;

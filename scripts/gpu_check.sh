@@ -19,5 +19,6 @@ run attn 600 tests/test_ops_gpu.py -k "attention or rope"
 run gemv 600 tests/test_ops_gpu.py -k "gemv"
 run misc 300 tests/test_ops_gpu.py -k "argmax or im2col"
 run model 1200 tests/test_model_gpu.py
+B2_DECODE_MEGA=0 run model_multikernel_decode 900 tests/test_model_gpu.py -k "golden or 7b or small or incremental"
 echo "=== smoke" | tee -a gpurun_out/summary.txt
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$? $(tail -n 1 gpurun_out/smoke.log)" | tee -a gpurun_out/summary.txt

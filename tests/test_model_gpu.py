@@ -280,6 +280,38 @@ def test_7b_layer_shapes_prefill_decode_consistency():
     eng.close()
 
 
+def test_decode_batch_above_8_uses_gemm_path_and_matches_oracle():
+    """B > 8 decode runs the skinny-M tcgen05 GEMM path (+ CUDA-graph replay); B <= 8 the persistent megakernel.
+    Both must agree with the oracle and with each other on the shared samples."""
+    cfg = O.CONFIGS["tiny"]
+    w = O.make_weights(cfg, seed=0)
+    eng = make_engine(cfg, w, max_batch=12, max_seq=96, max_images=4)
+    B, Lt, n = 10, 9, 5
+    ids, images = synth_inputs(cfg, B=B, Lt=Lt, seed=21, image_pos=2)
+    ref_toks, ref_steps = O.greedy_generate(w, ids, images, cfg, n, return_logits=True)
+    embeds, _, _, _ = O.prepare_multimodal(w, ids, images, cfg)
+    ref_logits, _ = O.llama_forward(w, embeds, cfg)
+    out = {}
+    for nb in (B, 4):
+        kv = eng.new_kv(nb, 96)
+        last = eng.prefill(kv, embeds[:nb].to(DEV), None, _b2.LOGITS_LAST)
+        _check(f"prefill last (B={nb})", last, ref_logits[:nb, -1])
+        first = eng.argmax(last)
+        rest = eng.decode_greedy(kv, first, n - 1)
+        out[nb] = torch.cat([first[None], rest]).t().cpu()
+        # teacher-forced step logits through the same path
+        kv.reset()
+        eng.prefill(kv, embeds[:nb].to(DEV), None, _b2.LOGITS_NONE)
+        for i in range(1, n):
+            lg = eng.decode_step(kv, ref_toks[:nb, i - 1].to(torch.int32))
+            _check(f"decode step {i} (B={nb})", lg, ref_steps[i][:nb], tol_max=0.06)
+        kv.close()
+    err_abs = 0.05 * float(ref_logits.std())
+    _assert_tokens(out[B].numpy(), ref_toks.numpy(), ref_steps.numpy(), err_abs)
+    _assert_tokens(out[4].numpy(), ref_toks[:4].numpy(), ref_steps[:, :4].numpy(), err_abs)
+    eng.close()
+
+
 def test_error_convention():
     cfg = O.CONFIGS["tiny"]
     w = O.make_weights(cfg, seed=0)
