@@ -126,7 +126,23 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference CPU path (oracle port) — bounded sample, extrapolated
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=torch.bfloat16):
+def pick_cpu_dtype():
+    """The reference runs whatever dtype the user loads; on a host without AMX-bf16, bf16 GEMMs are far slower
+    than fp32 in PyTorch. Time a small matmul in both and use the faster (the kinder baseline)."""
+    best, best_t = torch.float32, None
+    for dt in (torch.float32, torch.bfloat16):
+        a, b = torch.randn(512, 2048).to(dt), torch.randn(2048, 2048).to(dt)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        t = time.perf_counter() - t0
+        if best_t is None or t < best_t:
+            best, best_t = dt, t
+    return best
+
+
+def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=None):
     """Times the reference's algorithm (oracle/llava_oracle.py, HF-bf16 rounding points) on the host cores at
     the full LLaVA dims on a bounded sample: ViT+projector in full, `sample_layers` of the decoder layers for a
     full S-token prefill and `decode_steps` decode steps, lm_head measured separately; the per-layer time is
@@ -134,6 +150,8 @@ def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=torch.b
     from oracle import llava_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
+    if dtype is None:
+        dtype = pick_cpu_dtype()
     cfg = O.make_config(hidden=m["hidden"], inter=m["inter"], layers=sample_layers, heads=m["heads"])
     g = torch.Generator().manual_seed(0)
     w = {}
@@ -174,7 +192,7 @@ def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=torch.b
     t_decode_step = t_dec_0 + per_layer_dec * L
     total = t_enc + t_prefill + (N - 1) * t_decode_step
     return dict(value=(S + N) / total, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
-                sample=(f"oracle port (bf16, HF rounding points) at full {m['name']} dims: ViT+projector 1 image in full, "
+                sample=(f"oracle port ({str(dtype).replace('torch.', '')}, the faster of fp32/bf16 on this host) at full {m['name']} dims: ViT+projector 1 image in full, "
                         f"{sample_layers} of {L} decoder layers for an S={S} prefill (lm_head on all positions, as the "
                         f"reference does) and {decode_steps} decode steps, per-layer time extrapolated x{L}/{sample_layers}"),
                 breakdown=dict(encode_s=t_enc, prefill_s=t_prefill, decode_step_s=t_decode_step,
