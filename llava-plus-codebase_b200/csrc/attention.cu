@@ -453,9 +453,11 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(DecodeAttnParam
         __threadfence();
         const float* pb = p.partial + (size_t)bh * p.nsplit * (DA_D + 2);
         float m_all = -INFINITY;
+#pragma unroll 8
         for (int s = 0; s < p.nsplit; ++s) m_all = fmaxf(m_all, __ldcg(pb + (size_t)s * (DA_D + 2) + DA_D));
         float l_all = 0.f, o_all = 0.f;
-        for (int s = 0; s < p.nsplit; ++s) {
+#pragma unroll 8
+        for (int s = 0; s < p.nsplit; ++s) {  // independent loads: unrolled so they overlap instead of chaining
             const float ms = __ldcg(pb + (size_t)s * (DA_D + 2) + DA_D);
             const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - m_all);
             l_all += __ldcg(pb + (size_t)s * (DA_D + 2) + DA_D + 1) * w;

@@ -53,13 +53,17 @@ __device__ __forceinline__ void grid_sync(unsigned int* count, unsigned int* gen
     __syncthreads();
 }
 
-// hot per-phase state (lives in registers through the weight-streaming loop)
+// hot per-phase state (lives in registers through the weight-streaming loop).
+// Work decomposition of one GEMV phase: CTA c owns the logical rows [r_lo, r_lo + nrows) (even boundaries, so a
+// SwiGLU gate/up pair never straddles CTAs); inside the CTA the (row, 256-element chunk) units are flattened
+// row-major and split evenly over the 16 warps -> every warp streams the same number of bytes (+-512 B).
 struct GemvCtx {
     const __nv_bfloat16* W;
-    int K, act;
-    int nchunks, G, total_steps;
+    int K, act, nchunks;
+    int r_lo, nrows;   // logical rows of this CTA
+    int u_lo, u_hi;    // flattened unit range of this warp (local to the CTA)
 };
-// cold per-phase I/O, recomputed from the phase index where needed (prologue, per-item epilogue)
+// cold per-phase I/O, recomputed from the phase index where needed (prologue, epilogue)
 struct PhaseIO {
     const __nv_bfloat16* xin;
     const __nv_bfloat16* gamma;
@@ -71,32 +75,37 @@ struct PhaseIO {
 struct WarpId { int tid, lane, warp, gw, total_warps; };
 __device__ __forceinline__ PhaseIO mk_phase_io(const MegaParams& p, int ph);
 
-__device__ __forceinline__ void mk_item_rows(int act, int item, int& r0, int& r1) {
-    if (act == ACT_SWIGLU) { r0 = (item >> 6) * 128 + (item & 63); r1 = r0 + 64; }
-    else { r0 = item * 2; r1 = r0 + 1; }
+constexpr int MK_UB = 8;        // units (16 B loads per lane) per pipeline batch
+constexpr int MK_MAXROWS = 256; // max logical rows per CTA per phase (host-checked)
+
+// logical row -> physical weight row (SwiGLU: logical 2c / 2c+1 = gate / up row of channel c, block-64 interleaved)
+__device__ __forceinline__ int mk_phys_row(int act, int row) {
+    if (act == ACT_SWIGLU) {
+        const int c = row >> 1;
+        return (c >> 6) * 128 + (c & 63) + ((row & 1) ? 64 : 0);
+    }
+    return row;
 }
 
-__device__ __forceinline__ void mk_issue(const GemvCtx& c, int s, const WarpId& w, uint4 (&buf)[2][MK_U]) {
-    if (s < c.total_steps) {
-        const int item = w.gw + (s / c.G) * w.total_warps;
-        const int g = s % c.G;
-        int rr[2];
-        mk_item_rows(c.act, item, rr[0], rr[1]);
+// issue the loads of batch `bt` (units u_lo + 8*bt ...) — full definition of buf on every path
+__device__ __forceinline__ void mk_issue(const GemvCtx& c, int bt, const WarpId& w, uint4 (&buf)[MK_UB]) {
+    const int u0 = c.u_lo + bt * MK_UB;
+    if (u0 < c.u_hi) {
+        int row = u0 / c.nchunks;
+        int chunk = u0 - row * c.nchunks;
+        const __nv_bfloat16* wr = c.W + (size_t)mk_phys_row(c.act, c.r_lo + row) * c.K + w.lane * 8;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const __nv_bfloat16* wr = c.W + (size_t)rr[r] * c.K + w.lane * 8;
-#pragma unroll
-            for (int u = 0; u < MK_U; ++u) {
-                const int ch = g * MK_U + u;
-                buf[r][u] = (ch < c.nchunks) ? ld_stream_16(wr + ch * 256) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < MK_UB; ++j) {
+            buf[j] = (u0 + j < c.u_hi) ? ld_stream_16(wr + chunk * 256) : make_uint4(0, 0, 0, 0);
+            if (++chunk == c.nchunks) {
+                chunk = 0;
+                ++row;
+                wr = c.W + (size_t)mk_phys_row(c.act, c.r_lo + row) * c.K + w.lane * 8;
             }
         }
     } else {
-        // full (re)definition on every path: keeps the buffers' live ranges short for the register allocator
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int u = 0; u < MK_U; ++u) buf[r][u] = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < MK_UB; ++j) buf[j] = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -154,85 +163,125 @@ __device__ __forceinline__ void mk_prologue(const PhaseIO& c, int K, int B, floa
     __syncthreads();
 }
 
+// running state of a warp inside a phase
+struct RowState { int row, chunk; };
+
+// flush the finished (or cut-off) row `st.row`: complete rows go to sums[], partial rows to part_a / part_b
 template <int NB>
-__device__ __forceinline__ void mk_compute(const MegaParams& p, int ph, const GemvCtx& c, int s, int B,
-                                           const WarpId& w, const uint4 (&buf)[2][MK_U],
-                                           const __nv_bfloat16* xs, float (&acc)[2][NB]) {
-    if (s >= c.total_steps) return;
-    const int item = w.gw + (s / c.G) * w.total_warps;
-    const int g = s % c.G;
-    if (g == 0) {
+__device__ __forceinline__ void mk_flush(const GemvCtx& c, const WarpId& w, const RowState& st, bool row_ended,
+                                         float (&acc)[NB], float (*sums)[NB], float (*part_a)[NB],
+                                         float (*part_b)[NB]) {
+    const bool started_here = st.row * c.nchunks >= c.u_lo;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[0][b] = acc[1][b] = 0.f;
+    for (int b = 0; b < NB; ++b) {
+        const float v = warp_sum(acc[b]);
+        if (w.lane == 0) {
+            if (row_ended && started_here) sums[st.row][b] = v;       // whole row streamed by this warp
+            else if (!started_here) part_a[w.warp][b] = v;            // row began in an earlier warp
+            else part_b[w.warp][b] = v;                                // row continues in a later warp
+        }
+        acc[b] = 0.f;
     }
+}
+
+template <int NB>
+__device__ __forceinline__ void mk_compute(const GemvCtx& c, int bt, const WarpId& w, const uint4 (&buf)[MK_UB],
+                                           const __nv_bfloat16* xs, RowState& st, float (&acc)[NB],
+                                           float (*sums)[NB], float (*part_a)[NB], float (*part_b)[NB]) {
+    const int u0 = c.u_lo + bt * MK_UB;
+    if (u0 >= c.u_hi) return;
 #pragma unroll
-    for (int u = 0; u < MK_U; ++u) {
-        const int ch = g * MK_U + u;
-        if (ch < c.nchunks) {
-            float w0[8], w1[8];
-            unpack8(buf[0][u], w0);
-            unpack8(buf[1][u], w1);
-            const int koff = ch * 256 + w.lane * 8;
+    for (int j = 0; j < MK_UB; ++j) {
+        if (u0 + j < c.u_hi) {  // warp-uniform
+            float wf[8];
+            unpack8(buf[j], wf);
+            const int koff = st.chunk * 256 + w.lane * 8;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 float xf[8];
                 unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)b * c.K + koff), xf);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    acc[0][b] = fmaf(w0[e], xf[e], acc[0][b]);
-                    acc[1][b] = fmaf(w1[e], xf[e], acc[1][b]);
-                }
+                for (int e = 0; e < 8; ++e) acc[b] = fmaf(wf[e], xf[e], acc[b]);
             }
-        }
-    }
-    if (g == c.G - 1) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) { acc[0][b] = warp_sum(acc[0][b]); acc[1][b] = warp_sum(acc[1][b]); }
-        int r0, r1;
-        mk_item_rows(c.act, item, r0, r1);
-        const PhaseIO io = mk_phase_io(p, ph);
-        if (c.act == ACT_SWIGLU) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                if (w.lane == b && b < B) {
-                    const float gt = acc[0][b], up = acc[1][b];
-                    reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + item] =
-                        __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (w.lane == r * NB + b && b < B) {
-                        const int row = r == 0 ? r0 : r1;
-                        float y = acc[r][b];
-                        if (io.residual != nullptr) y += __bfloat162float(__ldcg(io.residual + (size_t)b * io.ld_out + row));
-                        if (io.out_fp32) reinterpret_cast<float*>(io.out)[(size_t)b * io.ld_out + row] = y;
-                        else reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + row] = __float2bfloat16_rn(y);
-                    }
-                }
+            if (++st.chunk == c.nchunks) {
+                mk_flush<NB>(c, w, st, true, acc, sums, part_a, part_b);
+                st.chunk = 0;
+                ++st.row;
             }
         }
     }
 }
 
-// RoPE + cache append + split-KV attention, one (b, head, split) item per warp; last warp of a (b, head) merges
-__device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLayer& Lw, const WarpId& w) {
+// value of logical local row r for batch b after the streaming loop (deterministic warp-order reduction)
+template <int NB>
+__device__ __forceinline__ float mk_row_value(const GemvCtx& c, int r, int b, int U, const float (*sums)[NB],
+                                              const float (*part_a)[NB], const float (*part_b)[NB]) {
+    const int first_u = r * c.nchunks, last_u = first_u + c.nchunks - 1;
+    const int w_first = min(MK_WARPS - 1, ((first_u + 1) * MK_WARPS - 1) / U);
+    const int w_last = min(MK_WARPS - 1, ((last_u + 1) * MK_WARPS - 1) / U);
+    if (w_first == w_last) return sums[r][b];
+    float v = 0.f;
+    for (int ww = w_first; ww <= w_last; ++ww) {
+        const int u_lo_w = (int)(((long long)U * ww) / MK_WARPS);
+        const int u_hi_w = (int)(((long long)U * (ww + 1)) / MK_WARPS);
+        if (u_hi_w > u_lo_w) v += (first_u < u_lo_w) ? part_a[ww][b] : part_b[ww][b];  // skip empty warps
+    }
+    return v;
+}
+
+// after the streaming loop: reduce partial rows, apply the epilogue, coalesced global writes
+template <int NB>
+__device__ __forceinline__ void mk_epilogue(const MegaParams& p, int ph, const GemvCtx& c, int B, const WarpId& w,
+                                            const float (*sums)[NB], const float (*part_a)[NB],
+                                            const float (*part_b)[NB]) {
+    const PhaseIO io = mk_phase_io(p, ph);
+    const int U = c.nrows * c.nchunks;
+    if (c.act == ACT_SWIGLU) {
+        const int nch = c.nrows >> 1;
+        for (int idx = w.tid; idx < nch * B; idx += MK_THREADS) {
+            const int b = idx / nch, ch = idx - b * nch;
+            const float gt = mk_row_value<NB>(c, 2 * ch, b, U, sums, part_a, part_b);
+            const float up = mk_row_value<NB>(c, 2 * ch + 1, b, U, sums, part_a, part_b);
+            reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + (c.r_lo >> 1) + ch] =
+                __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
+        }
+    } else {
+        for (int idx = w.tid; idx < c.nrows * B; idx += MK_THREADS) {
+            const int b = idx / c.nrows, r = idx - b * c.nrows;
+            float y = mk_row_value<NB>(c, r, b, U, sums, part_a, part_b);
+            const size_t o = (size_t)b * io.ld_out + c.r_lo + r;
+            if (io.residual != nullptr) y += __bfloat162float(__ldcg(io.residual + o));
+            if (io.out_fp32) reinterpret_cast<float*>(io.out)[o] = y;
+            else reinterpret_cast<__nv_bfloat16*>(io.out)[o] = __float2bfloat16_rn(y);
+        }
+    }
+}
+
+// RoPE + cache append + split-KV attention.
+// (b, head) pairs are spread over the grid: with pairs <= #CTAs, G = #CTAs / pairs CTAs share one pair (split-KV
+// across CTAs, merged by the last CTA to arrive — only G partials, G = 4 at B = 1); otherwise each CTA walks
+// pairs one after the other. Inside a CTA the 16 warps split the key range (half-warp per 256 B K/V row,
+// online softmax in registers) and merge through shared memory, so no long serial merge sits on the critical path.
+__device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLayer& Lw, const WarpId& w,
+                                             float (*s_part)[MK_D + 2], int* s_flag) {
     const int h = p.h, H = p.H;
-    const int n_items = p.B * H * p.nsplit;
+    const int pairs = p.B * H;
+    const int grid = gridDim.x;
+    const int G = pairs <= grid ? grid / pairs : 1;
     const int lane = w.lane;
     const int hw = lane >> 4, c = lane & 15;
-    for (int item = w.gw; item < n_items; item += w.total_warps) {
-        const int split = item % p.nsplit;
-        const int bh = item / p.nsplit;
-        const int head = bh % H, b = bh / H;
+    const int split = pairs <= grid ? (int)blockIdx.x % G : 0;
+    for (int pair = pairs <= grid ? (int)blockIdx.x / G : (int)blockIdx.x; pair < pairs;
+         pair += (pairs <= grid ? pairs : grid)) {  // CTA-uniform loop
+        const int head = pair % H, b = pair / H;
         const int pos = p.cur_len[b];
         const int total = pos + 1;
-        const int chunk = (total + p.nsplit - 1) / p.nsplit;
-        const int k_begin = split * chunk;
-        const int k_end = min(k_begin + chunk, total);
+        const int cchunk = (total + G - 1) / G;
+        const int cb = split * cchunk;
+        const int ce = min(cb + cchunk, total);
+        const int wchunk = (max(ce - cb, 0) + MK_WARPS - 1) / MK_WARPS;
+        const int k_begin = cb + w.warp * wchunk;
+        const int k_end = min(k_begin + wchunk, ce);
         const __nv_bfloat16* qrow = p.qkv + (size_t)b * 3 * h + head * MK_D;
         float qreg[8], knew[8], vnew[8];
         {
@@ -250,9 +299,9 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
                 const float inv_freq = exp2f(-(2.0f * i / MK_D) * log2f(p.theta));
                 float sv, cv;
                 sincosf(pos * inv_freq, &sv, &cv);
-                const float cb = round_bf16(cv), sb = round_bf16(sv);
-                qreg[e] = round_bf16(round_bf16(qa[e] * cb) + round_bf16(sign * qb[e] * sb));
-                knew[e] = round_bf16(round_bf16(ka[e] * cb) + round_bf16(sign * kb[e] * sb));
+                const float cbf = round_bf16(cv), sbf = round_bf16(sv);
+                qreg[e] = round_bf16(round_bf16(qa[e] * cbf) + round_bf16(sign * qb[e] * sbf));
+                knew[e] = round_bf16(round_bf16(ka[e] * cbf) + round_bf16(sign * kb[e] * sbf));
             }
         }
         const size_t cbase = ((size_t)b * H + head) * p.Smax * MK_D;
@@ -325,39 +374,57 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
             l_run = l_run * w_s + l_o * w_o;
             m_run = m_c;
         }
-        float* part = p.attn_partial + (size_t)item * (MK_D + 2);
         if (hw == 0) {
-            // partial rows are (128+2) floats: 8-byte aligned only -> float2 stores
-            float2* pp = reinterpret_cast<float2*>(part + c * 8);
-            pp[0] = make_float2(av[0], av[1]); pp[1] = make_float2(av[2], av[3]);
-            pp[2] = make_float2(av[4], av[5]); pp[3] = make_float2(av[6], av[7]);
-            if (c == 0) { part[MK_D] = m_run; part[MK_D + 1] = l_run; }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s_part[w.warp][c * 8 + e] = av[e];
+            if (c == 0) { s_part[w.warp][MK_D] = m_run; s_part[w.warp][MK_D + 1] = l_run; }
         }
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) last = (atomicAdd(&p.attn_counters[bh], 1) == p.nsplit - 1) ? 1 : 0;
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence();
-            const float* pb = p.attn_partial + (size_t)bh * p.nsplit * (MK_D + 2);
-            float m_all = -INFINITY;
-            for (int s = 0; s < p.nsplit; ++s) m_all = fmaxf(m_all, __ldcg(pb + (size_t)s * (MK_D + 2) + MK_D));
-            float l_all = 0.f, o4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int s = 0; s < p.nsplit; ++s) {
-                const float ms = __ldcg(pb + (size_t)s * (MK_D + 2) + MK_D);
-                const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - m_all);
-                l_all += __ldcg(pb + (size_t)s * (MK_D + 2) + MK_D + 1) * wgt;
-                const float2 oa = __ldcg(reinterpret_cast<const float2*>(pb + (size_t)s * (MK_D + 2) + lane * 4));
-                const float2 ob = __ldcg(reinterpret_cast<const float2*>(pb + (size_t)s * (MK_D + 2) + lane * 4 + 2));
-                o4[0] += oa.x * wgt; o4[1] += oa.y * wgt; o4[2] += ob.x * wgt; o4[3] += ob.y * wgt;
+        __syncthreads();
+        // ---- merge the 16 warps of this CTA (thread d owns output element d) ----
+        float m_cta = -INFINITY, l_cta = 0.f, o_cta = 0.f;
+        if (w.tid < MK_D) {
+#pragma unroll
+            for (int i = 0; i < MK_WARPS; ++i) m_cta = fmaxf(m_cta, s_part[i][MK_D]);
+#pragma unroll
+            for (int i = 0; i < MK_WARPS; ++i) {
+                const float ms = s_part[i][MK_D];
+                const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - m_cta);
+                l_cta += s_part[i][MK_D + 1] * wgt;
+                o_cta += s_part[i][w.tid] * wgt;
             }
-            const float inv = 1.f / l_all;
-            __nv_bfloat16* op = p.attn + (size_t)b * h + head * MK_D + lane * 4;
-            *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16(o4[0] * inv, o4[1] * inv),
-                                                       pack_bf16(o4[2] * inv, o4[3] * inv));
-            if (lane == 0) p.attn_counters[bh] = 0;
         }
+        if (G == 1) {
+            if (w.tid < MK_D)
+                p.attn[(size_t)b * h + head * MK_D + w.tid] = __float2bfloat16_rn(o_cta / l_cta);
+        } else {
+            float* part = p.attn_partial + ((size_t)pair * G + split) * (MK_D + 2);
+            if (w.tid < MK_D) {
+                part[w.tid] = o_cta;
+                if (w.tid == 0) { part[MK_D] = m_cta; part[MK_D + 1] = l_cta; }
+            }
+            __threadfence();
+            __syncthreads();
+            if (w.tid == 0) *s_flag = (atomicAdd(&p.attn_counters[pair], 1) == G - 1) ? 1 : 0;
+            __syncthreads();
+            if (*s_flag) {  // last CTA of this (b, head): merge the G partials
+                __threadfence();
+                if (w.tid < MK_D) {
+                    const float* pb = p.attn_partial + (size_t)pair * G * (MK_D + 2);
+                    float m_all = -INFINITY;
+                    for (int sidx = 0; sidx < G; ++sidx) m_all = fmaxf(m_all, __ldcg(pb + (size_t)sidx * (MK_D + 2) + MK_D));
+                    float l_all = 0.f, o_all = 0.f;
+                    for (int sidx = 0; sidx < G; ++sidx) {
+                        const float ms = __ldcg(pb + (size_t)sidx * (MK_D + 2) + MK_D);
+                        const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - m_all);
+                        l_all += __ldcg(pb + (size_t)sidx * (MK_D + 2) + MK_D + 1) * wgt;
+                        o_all += __ldcg(pb + (size_t)sidx * (MK_D + 2) + w.tid) * wgt;
+                    }
+                    p.attn[(size_t)b * h + head * MK_D + w.tid] = __float2bfloat16_rn(o_all / l_all);
+                    if (w.tid == 0) p.attn_counters[pair] = 0;
+                }
+            }
+        }
+        __syncthreads();  // s_part / s_flag are reused by the next pair
     }
 }
 
@@ -384,10 +451,12 @@ __device__ __forceinline__ GemvCtx mk_phase_ctx(const MegaParams& p, int ph, con
     else if (k == 3) { c.W = p.layers[l].wgu; N = 2 * p.I; c.K = p.h; c.act = ACT_SWIGLU; }
     else { c.W = p.layers[l].wd; N = p.h; c.K = p.I; }
     c.nchunks = c.K >> 8;
-    c.G = (c.nchunks + MK_U - 1) / MK_U;
-    const int n_items = N >> 1;
-    const int n_my = w.gw < n_items ? (n_items - w.gw + w.total_warps - 1) / w.total_warps : 0;
-    c.total_steps = n_my * c.G;
+    const long long pairs = N >> 1;
+    c.r_lo = 2 * (int)((pairs * blockIdx.x) / gridDim.x);
+    c.nrows = 2 * (int)((pairs * (blockIdx.x + 1)) / gridDim.x) - c.r_lo;
+    const long long U = (long long)c.nrows * c.nchunks;
+    c.u_lo = (int)((U * w.warp) / MK_WARPS);
+    c.u_hi = (int)((U * (w.warp + 1)) / MK_WARPS);
     return c;
 }
 
@@ -399,6 +468,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     __shared__ float s_rstd[NB];
     __shared__ float s_av[MK_WARPS];
     __shared__ int s_ai[MK_WARPS];
+    __shared__ float s_part[MK_WARPS][MK_D + 2];
+    __shared__ int s_flag;
+    __shared__ float s_sums[MK_MAXROWS][NB];
+    __shared__ float s_pa[MK_WARPS][NB];
+    __shared__ float s_pb[MK_WARPS][NB];
 
     WarpId w;
     w.tid = threadIdx.x; w.lane = w.tid & 31; w.warp = w.tid >> 5;
@@ -406,12 +480,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     w.total_warps = gridDim.x * MK_WARPS;
     const int B = p.B;
 
-    uint4 bufA[2][MK_U], bufB[2][MK_U];
-    float acc[2][NB];
+    uint4 bufA[MK_UB], bufB[MK_UB];
+    float acc[NB];
 
     // ---------------- phase "-1": x = embed_tokens[tok]; layer-0 QKV weights already in flight ----------------
     GemvCtx cur = mk_phase_ctx(p, 0, w);
     mk_issue(cur, 0, w, bufA);
+    mk_issue(cur, 1, w, bufB);
     if (blockIdx.x < B) {
         int t = p.tok[blockIdx.x];
         t = t < 0 ? 0 : (t >= p.V ? p.V - 1 : t);
@@ -425,17 +500,27 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 #pragma unroll 1
     for (int ph = 0; ph < n_phases; ++ph) {
         if (ph % 5 == 1 && ph < 5 * p.L) {
-            mk_attention(p, p.layers[ph / 5], w);
+            mk_attention(p, p.layers[ph / 5], w, s_part, &s_flag);
         } else {
             // the first step's weights were issued (into bufA) before the preceding barrier
             mk_prologue<NB>(mk_phase_io(p, ph), cur.K, B, p.eps, w, xs, s_red, s_rstd);
+            RowState st;
+            st.row = cur.u_lo / cur.nchunks;
+            st.chunk = cur.u_lo - st.row * cur.nchunks;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+            const int n_batches = (cur.u_hi - cur.u_lo + MK_UB - 1) / MK_UB;
+            // batches 0 and 1 were issued (bufA, bufB) before the preceding barrier
 #pragma unroll 1
-            for (int s = 0; s < cur.total_steps; s += 2) {
-                mk_issue(cur, s + 1, w, bufB);
-                mk_compute<NB>(p, ph, cur, s, B, w, bufA, xs, acc);
-                mk_issue(cur, s + 2, w, bufA);
-                mk_compute<NB>(p, ph, cur, s + 1, B, w, bufB, xs, acc);
+            for (int bt = 0; bt < n_batches; bt += 2) {
+                mk_compute<NB>(cur, bt, w, bufA, xs, st, acc, s_sums, s_pa, s_pb);
+                mk_issue(cur, bt + 2, w, bufA);
+                mk_compute<NB>(cur, bt + 1, w, bufB, xs, st, acc, s_sums, s_pa, s_pb);
+                mk_issue(cur, bt + 3, w, bufB);
             }
+            if (st.chunk != 0) mk_flush<NB>(cur, w, st, false, acc, s_sums, s_pa, s_pb);  // row cut by the warp boundary
+            __syncthreads();
+            mk_epilogue<NB>(p, ph, cur, B, w, s_sums, s_pa, s_pb);
         }
         // prefetch the next GEMV phase's first weights across the barrier (weights don't depend on activations)
         int nxt = ph + 1;
@@ -443,9 +528,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
         if (nxt >= 0 && nxt < n_phases) {
             cur = mk_phase_ctx(p, nxt, w);
             mk_issue(cur, 0, w, bufA);
+            mk_issue(cur, 1, w, bufB);
         } else {
-            cur.total_steps = 0;
-            mk_issue(cur, 0, w, bufA);  // defines bufA (zeros): nothing is carried across the attention phase
+            cur.u_lo = cur.u_hi = 0;
+            mk_issue(cur, 0, w, bufA);  // defines the buffers (zeros): nothing is carried across the attention phase
+            mk_issue(cur, 1, w, bufB);
         }
         grid_sync(p.bar_count, p.bar_gen, gridDim.x);
     }
@@ -499,14 +586,30 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 
 }  // namespace
 
+// dynamic activation tile [NB][max(h, I)] bf16 + ~(MK_MAXROWS + 2*16 + 16 + 1) * NB floats of static tables
+bool decode_mega_fits(int B, int h, int I) {
+    if (B < 1 || B > 8) return false;
+    const int NB = B == 1 ? 1 : (B == 2 ? 2 : (B <= 4 ? 4 : 8));
+    const size_t dyn = (size_t)NB * (h > I ? h : I) * 2;
+    const size_t stat = (size_t)(MK_MAXROWS + 3 * MK_WARPS + 1) * NB * 4 + MK_WARPS * (MK_D + 2) * 4 + 512;
+    return dyn + stat <= 227 * 1024;
+}
+
 int decode_mega(const MegaParams& p, cudaStream_t stream) {
     B2_CHECK_ARG(p.B >= 1 && p.B <= 8, "decode_mega: batch must be 1..8");
     B2_CHECK_ARG(p.h % 256 == 0 && p.I % 256 == 0 && p.V % 2 == 0 && p.h / p.H == MK_D,
                  "decode_mega: unsupported dims h=%d I=%d V=%d H=%d", p.h, p.I, p.V, p.H);
+    {
+        const int grid = num_sms();
+        const int nmax = p.V > 3 * p.h ? (p.V > 2 * p.I ? p.V : 2 * p.I) : (3 * p.h > 2 * p.I ? 3 * p.h : 2 * p.I);
+        B2_CHECK_ARG(2 * ((nmax / 2 + grid - 1) / grid) + 2 <= MK_MAXROWS,
+                     "decode_mega: %d output rows per CTA exceed the shared-memory row table", nmax / grid);
+    }
     const int NB = p.B == 1 ? 1 : (p.B == 2 ? 2 : (p.B <= 4 ? 4 : 8));
     const int kmax = p.h > p.I ? p.h : p.I;
     const size_t smem = (size_t)NB * kmax * 2;
-    B2_CHECK_ARG(smem <= 224 * 1024, "decode_mega: activations do not fit shared memory (B=%d K=%d)", p.B, kmax);
+    B2_CHECK_ARG(decode_mega_fits(p.B, p.h, p.I), "decode_mega: activations do not fit shared memory (B=%d K=%d)",
+                 p.B, kmax);
     void* fn = nullptr;
     switch (NB) {
         case 1: fn = (void*)decode_mega_kernel<1>; break;

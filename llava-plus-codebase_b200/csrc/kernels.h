@@ -110,6 +110,7 @@ struct MegaParams {
 };
 // one launch = embed -> all layers -> lm_head -> argmax -> token store; cur_len/step_counter advance on device
 int decode_mega(const MegaParams& p, cudaStream_t stream);
+bool decode_mega_fits(int B, int h, int I);
 
 // ---- misc (misc_ops.cu) ----------------------------------------------------------------------------
 // out[r, :] = src_index[r] >= 0 ? table[src_index[r]] : (src_index[r] == INT32_MIN ? 0 : feats[-src_index[r]-1])

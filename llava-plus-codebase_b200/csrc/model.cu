@@ -416,13 +416,14 @@ int join_stream(b2_kv* kv, cudaStream_t st, cudaStream_t run) {
 }
 
 // run one step, through the cached CUDA graph when possible
-bool use_mega(int B) {
+bool use_mega(const b2_model* m, int B) {
+    if (!decode_mega_fits(B, m->d.hidden, m->d.inter)) return false;
     static int flag = -1;
     if (flag < 0) {
         const char* e = getenv("B2_DECODE_MEGA");
         flag = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    return flag == 1 && B <= 8;
+    return flag == 1;
 }
 
 int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
@@ -447,7 +448,7 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
 
 int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     // B <= 8: one persistent cooperative launch per token (no graph needed: launches queue asynchronously)
-    if (use_mega(B)) return decode_step_mega(m, kv, B, st);
+    if (use_mega(m, B)) return decode_step_mega(m, kv, B, st);
     if (kv->warm_B != B) {
         // first step for this batch size runs eagerly: sets function attributes, resolves driver entry points
         if (kv->graph) { cudaGraphExecDestroy(kv->graph); kv->graph = nullptr; kv->graph_B = 0; }
@@ -713,7 +714,7 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
         cudaMemset(kv->mega_sync.p, 0, 64);
     }
     if ((r = kv->out_tokens.alloc((size_t)kv->out_capacity * max_batch * 4)) != 0 ||
-        (r = kv->attn_partial.alloc((size_t)max_batch * m->d.heads * max_split * (128 + 2) * 4)) != 0 ||
+        (r = kv->attn_partial.alloc(((size_t)max_batch * m->d.heads * max_split + 1024) * (128 + 2) * 4)) != 0 ||
         (r = kv->attn_counters.alloc((size_t)max_batch * m->d.heads * 4)) != 0) {
         b2_kv_destroy(kv);
         return r;

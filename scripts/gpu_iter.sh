@@ -1,7 +1,10 @@
 #!/bin/bash
-# quick iteration: model tests (mega + multi-kernel decode) and a short bench
+# quick iteration: model tests (mega + multi-kernel decode) and short benches
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD:$PWD/llava-plus-codebase_b200:$PYTHONPATH
 timeout 900 python -m pytest tests/test_model_gpu.py -q --tb=short -x -p no:cacheprovider > gpurun_out/model.log 2>&1; echo "model rc=$? $(tail -n 1 gpurun_out/model.log)"; grep -E "^(FAILED|ERROR|E  )" gpurun_out/model.log | head -20
-timeout 600 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_iter.json')); print({k:d[k] for k in ('value','ms_per_step','breakdown','gpu_launches')}); print(d['roofline']['frac'], d['e2e'])" ; tail -n 3 gpurun_out/bench_iter.err
+B2_DECODE_MEGA=0 timeout 900 python -m pytest tests/test_model_gpu.py -q --tb=short -x -p no:cacheprovider -k "golden or 7b or small or incremental" > gpurun_out/model_mk.log 2>&1; echo "model(multi-kernel) rc=$? $(tail -n 1 gpurun_out/model_mk.log)"; grep -E "^(FAILED|ERROR|E  )" gpurun_out/model_mk.log | head -20
+for mode in 1 0; do
+B2_DECODE_MEGA=$mode timeout 600 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/bench_iter_$mode.json 2> gpurun_out/bench_iter_$mode.err; echo "bench mega=$mode rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_iter_$mode.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['breakdown']); print(d['roofline']['frac'], d['e2e'])" ; tail -n 3 gpurun_out/bench_iter_$mode.err
+done
