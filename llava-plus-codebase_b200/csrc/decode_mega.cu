@@ -54,14 +54,22 @@ __device__ __forceinline__ void grid_sync(unsigned int* count, unsigned int* gen
 }
 
 // hot per-phase state (lives in registers through the weight-streaming loop).
-// Work decomposition of one GEMV phase: CTA c owns the logical rows [r_lo, r_lo + nrows) (even boundaries, so a
-// SwiGLU gate/up pair never straddles CTAs); inside the CTA the (row, 256-element chunk) units are flattened
-// row-major and split evenly over the 16 warps -> every warp streams the same number of bytes (+-512 B).
+// Work decomposition of one GEMV phase:
+//   * output rows are grouped into logical 8-row blocks (SwiGLU: 4 gate rows + the 4 up rows of the same
+//     channels); CTA c owns the contiguous block range [rb_lo, rb_lo + nb);
+//   * inside the CTA the 16 warps split K (in 32-element slices), so every warp streams exactly the same number
+//     of bytes for every block, and the 16 partial sums per output are reduced through shared memory in a fixed
+//     order (deterministic);
+//   * the arithmetic runs on the tensor cores as mma.sync.m16n8k16 (bf16 x bf16 -> fp32) with the activations
+//     as the A operand (rows = batch, zero padded to 16) and 8 weight rows as the B operand. One 16-byte load per
+//     lane (row g = lane/4, 8 consecutive k at (lane%4)*8) feeds TWO MMAs with no unpacking: the k index is
+//     permuted consistently on both operands, which a dot product does not care about. ~5 instructions per
+//     16 B of weights instead of ~40 for the scalar bf16->fp32 FMA loop (the round-1 kernel was issue-bound).
 struct GemvCtx {
     const __nv_bfloat16* W;
-    int K, act, nchunks;
-    int r_lo, nrows;   // logical rows of this CTA
-    int u_lo, u_hi;    // flattened unit range of this warp (local to the CTA)
+    int K, act;
+    int rb_lo, nb;       // logical 8-row blocks of this CTA
+    int ks_lo, ks_len;   // this warp's K slice, in 32-element blocks
 };
 // cold per-phase I/O, recomputed from the phase index where needed (prologue, epilogue)
 struct PhaseIO {
@@ -75,32 +83,35 @@ struct PhaseIO {
 struct WarpId { int tid, lane, warp, gw, total_warps; };
 __device__ __forceinline__ PhaseIO mk_phase_io(const MegaParams& p, int ph);
 
-constexpr int MK_UB = 8;        // units (16 B loads per lane) per pipeline batch
-constexpr int MK_MAXROWS = 256; // max logical rows per CTA per phase (host-checked)
+constexpr int MK_UB = 8;      // units (16 B loads per lane) per pipeline batch
+constexpr int MK_MAXNB = 32;  // max 8-row blocks per CTA per phase (host-checked)
 
-// logical row -> physical weight row (SwiGLU: logical 2c / 2c+1 = gate / up row of channel c, block-64 interleaved)
-__device__ __forceinline__ int mk_phys_row(int act, int row) {
-    if (act == ACT_SWIGLU) {
-        const int c = row >> 1;
-        return (c >> 6) * 128 + (c & 63) + ((row & 1) ? 64 : 0);
+// physical weight row streamed by lane-group g (0..7) of logical block `blk`
+__device__ __forceinline__ int mk_phys_row(int act, int blk, int g) {
+    if (act == ACT_SWIGLU) {  // block-64 interleaved gate/up: g<4 -> gate of channel 4*blk+g, g>=4 -> up of 4*blk+g-4
+        const int ch = blk * 4 + (g & 3);
+        return (ch >> 6) * 128 + (ch & 63) + ((g >> 2) ? 64 : 0);
     }
-    return row;
+    return blk * 8 + g;
 }
 
-// issue the loads of batch `bt` (units u_lo + 8*bt ...) — full definition of buf on every path
+// issue the loads of batch `bt` (units 8*bt ...; unit u = (block u / ks_len, k-slice element u % ks_len)) —
+// a full definition of buf on every path
 __device__ __forceinline__ void mk_issue(const GemvCtx& c, int bt, const WarpId& w, uint4 (&buf)[MK_UB]) {
-    const int u0 = c.u_lo + bt * MK_UB;
-    if (u0 < c.u_hi) {
-        int row = u0 / c.nchunks;
-        int chunk = u0 - row * c.nchunks;
-        const __nv_bfloat16* wr = c.W + (size_t)mk_phys_row(c.act, c.r_lo + row) * c.K + w.lane * 8;
+    const int u0 = bt * MK_UB;
+    const int U = c.nb * c.ks_len;
+    if (u0 < U) {
+        const int g = w.lane >> 2, t = w.lane & 3;
+        int rb = u0 / c.ks_len;
+        int kk = u0 - rb * c.ks_len;
+        const __nv_bfloat16* wr = c.W + (size_t)mk_phys_row(c.act, c.rb_lo + rb, g) * c.K + (size_t)c.ks_lo * 32 + t * 8;
 #pragma unroll
         for (int j = 0; j < MK_UB; ++j) {
-            buf[j] = (u0 + j < c.u_hi) ? ld_stream_16(wr + chunk * 256) : make_uint4(0, 0, 0, 0);
-            if (++chunk == c.nchunks) {
-                chunk = 0;
-                ++row;
-                wr = c.W + (size_t)mk_phys_row(c.act, c.r_lo + row) * c.K + w.lane * 8;
+            buf[j] = (u0 + j < U) ? ld_stream_16(wr + kk * 32) : make_uint4(0, 0, 0, 0);
+            if (++kk == c.ks_len) {
+                kk = 0;
+                ++rb;
+                wr = c.W + (size_t)mk_phys_row(c.act, c.rb_lo + rb, g) * c.K + (size_t)c.ks_lo * 32 + t * 8;
             }
         }
     } else {
@@ -164,92 +175,78 @@ __device__ __forceinline__ void mk_prologue(const PhaseIO& c, int K, int B, floa
 }
 
 // running state of a warp inside a phase
-struct RowState { int row, chunk; };
+struct RowState { int rb, kk; };
 
-// flush the finished (or cut-off) row `st.row`: complete rows go to sums[], partial rows to part_a / part_b
-template <int NB>
-__device__ __forceinline__ void mk_flush(const GemvCtx& c, const WarpId& w, const RowState& st, bool row_ended,
-                                         float (&acc)[NB], float (*sums)[NB], float (*part_a)[NB],
-                                         float (*part_b)[NB]) {
-    const bool started_here = st.row * c.nchunks >= c.u_lo;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const float v = warp_sum(acc[b]);
-        if (w.lane == 0) {
-            if (row_ended && started_here) sums[st.row][b] = v;       // whole row streamed by this warp
-            else if (!started_here) part_a[w.warp][b] = v;            // row began in an earlier warp
-            else part_b[w.warp][b] = v;                                // row continues in a later warp
-        }
-        acc[b] = 0.f;
-    }
+__device__ __forceinline__ void mk_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    // A rows 8..15 (a1, a3) are the zero padding of the batch dimension
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
 
+// s_part layout: [warp][block][b][8 rows] fp32
 template <int NB>
-__device__ __forceinline__ void mk_compute(const GemvCtx& c, int bt, const WarpId& w, const uint4 (&buf)[MK_UB],
-                                           const __nv_bfloat16* xs, RowState& st, float (&acc)[NB],
-                                           float (*sums)[NB], float (*part_a)[NB], float (*part_b)[NB]) {
-    const int u0 = c.u_lo + bt * MK_UB;
-    if (u0 >= c.u_hi) return;
+__device__ __forceinline__ void mk_compute(const GemvCtx& c, int bt, int B, const WarpId& w,
+                                           const uint4 (&buf)[MK_UB], const __nv_bfloat16* xs, RowState& st,
+                                           float (&acc)[4], float* s_part) {
+    const int u0 = bt * MK_UB;
+    const int U = c.nb * c.ks_len;
+    if (u0 >= U) return;
+    const int g = w.lane >> 2, t = w.lane & 3;
 #pragma unroll
     for (int j = 0; j < MK_UB; ++j) {
-        if (u0 + j < c.u_hi) {  // warp-uniform
-            float wf[8];
-            unpack8(buf[j], wf);
-            const int koff = st.chunk * 256 + w.lane * 8;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                float xf[8];
-                unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)b * c.K + koff), xf);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[b] = fmaf(wf[e], xf[e], acc[b]);
-            }
-            if (++st.chunk == c.nchunks) {
-                mk_flush<NB>(c, w, st, true, acc, sums, part_a, part_b);
-                st.chunk = 0;
-                ++st.row;
+        if (u0 + j < U) {  // warp-uniform
+            uint4 xv = make_uint4(0, 0, 0, 0);
+            if (g < B) xv = *reinterpret_cast<const uint4*>(xs + (size_t)g * c.K + (size_t)(c.ks_lo + st.kk) * 32 + t * 8);
+            mk_mma(acc, xv.x, xv.y, buf[j].x, buf[j].y);
+            mk_mma(acc, xv.z, xv.w, buf[j].z, buf[j].w);
+            if (++st.kk == c.ks_len) {
+                // acc[0], acc[1] = D[batch g][weight rows 2t, 2t+1] over this warp's K slice
+                if (g < NB) {
+                    float2* dst = reinterpret_cast<float2*>(s_part + (((size_t)w.warp * MK_MAXNB + st.rb) * NB + g) * 8 + t * 2);
+                    *dst = make_float2(acc[0], acc[1]);
+                }
+                acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+                st.kk = 0;
+                ++st.rb;
             }
         }
     }
 }
 
-// value of logical local row r for batch b after the streaming loop (deterministic warp-order reduction)
 template <int NB>
-__device__ __forceinline__ float mk_row_value(const GemvCtx& c, int r, int b, int U, const float (*sums)[NB],
-                                              const float (*part_a)[NB], const float (*part_b)[NB]) {
-    const int first_u = r * c.nchunks, last_u = first_u + c.nchunks - 1;
-    const int w_first = min(MK_WARPS - 1, ((first_u + 1) * MK_WARPS - 1) / U);
-    const int w_last = min(MK_WARPS - 1, ((last_u + 1) * MK_WARPS - 1) / U);
-    if (w_first == w_last) return sums[r][b];
+__device__ __forceinline__ float mk_row_value(const float* s_part, int nk32, int rb, int b, int r) {
     float v = 0.f;
-    for (int ww = w_first; ww <= w_last; ++ww) {
-        const int u_lo_w = (int)(((long long)U * ww) / MK_WARPS);
-        const int u_hi_w = (int)(((long long)U * (ww + 1)) / MK_WARPS);
-        if (u_hi_w > u_lo_w) v += (first_u < u_lo_w) ? part_a[ww][b] : part_b[ww][b];  // skip empty warps
+#pragma unroll
+    for (int ww = 0; ww < MK_WARPS; ++ww) {  // fixed order; warps whose K slice is empty (K < 512) wrote nothing
+        const bool has = (nk32 * (ww + 1)) / MK_WARPS > (nk32 * ww) / MK_WARPS;
+        if (has) v += s_part[(((size_t)ww * MK_MAXNB + rb) * NB + b) * 8 + r];
     }
     return v;
 }
 
-// after the streaming loop: reduce partial rows, apply the epilogue, coalesced global writes
+// after the streaming loop: reduce the 16 K-slices, apply the epilogue, coalesced global writes
 template <int NB>
 __device__ __forceinline__ void mk_epilogue(const MegaParams& p, int ph, const GemvCtx& c, int B, const WarpId& w,
-                                            const float (*sums)[NB], const float (*part_a)[NB],
-                                            const float (*part_b)[NB]) {
+                                            const float* s_part) {
     const PhaseIO io = mk_phase_io(p, ph);
-    const int U = c.nrows * c.nchunks;
     if (c.act == ACT_SWIGLU) {
-        const int nch = c.nrows >> 1;
+        const int nch = c.nb * 4;
         for (int idx = w.tid; idx < nch * B; idx += MK_THREADS) {
-            const int b = idx / nch, ch = idx - b * nch;
-            const float gt = mk_row_value<NB>(c, 2 * ch, b, U, sums, part_a, part_b);
-            const float up = mk_row_value<NB>(c, 2 * ch + 1, b, U, sums, part_a, part_b);
-            reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + (c.r_lo >> 1) + ch] =
+            const int b = idx / nch, r = idx - b * nch;
+            const int rb = r >> 2, q = r & 3;
+            const float gt = mk_row_value<NB>(s_part, c.K >> 5, rb, b, q);
+            const float up = mk_row_value<NB>(s_part, c.K >> 5, rb, b, q + 4);
+            reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + (size_t)c.rb_lo * 4 + r] =
                 __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
         }
     } else {
-        for (int idx = w.tid; idx < c.nrows * B; idx += MK_THREADS) {
-            const int b = idx / c.nrows, r = idx - b * c.nrows;
-            float y = mk_row_value<NB>(c, r, b, U, sums, part_a, part_b);
-            const size_t o = (size_t)b * io.ld_out + c.r_lo + r;
+        const int nr = c.nb * 8;
+        for (int idx = w.tid; idx < nr * B; idx += MK_THREADS) {
+            const int b = idx / nr, r = idx - b * nr;
+            float y = mk_row_value<NB>(s_part, c.K >> 5, r >> 3, b, r & 7);
+            const size_t o = (size_t)b * io.ld_out + (size_t)c.rb_lo * 8 + r;
             if (io.residual != nullptr) y += __bfloat162float(__ldcg(io.residual + o));
             if (io.out_fp32) reinterpret_cast<float*>(io.out)[o] = y;
             else reinterpret_cast<__nv_bfloat16*>(io.out)[o] = __float2bfloat16_rn(y);
@@ -450,13 +447,12 @@ __device__ __forceinline__ GemvCtx mk_phase_ctx(const MegaParams& p, int ph, con
     else if (k == 2) { c.W = p.layers[l].wo; N = p.h; c.K = p.h; }
     else if (k == 3) { c.W = p.layers[l].wgu; N = 2 * p.I; c.K = p.h; c.act = ACT_SWIGLU; }
     else { c.W = p.layers[l].wd; N = p.h; c.K = p.I; }
-    c.nchunks = c.K >> 8;
-    const long long pairs = N >> 1;
-    c.r_lo = 2 * (int)((pairs * blockIdx.x) / gridDim.x);
-    c.nrows = 2 * (int)((pairs * (blockIdx.x + 1)) / gridDim.x) - c.r_lo;
-    const long long U = (long long)c.nrows * c.nchunks;
-    c.u_lo = (int)((U * w.warp) / MK_WARPS);
-    c.u_hi = (int)((U * (w.warp + 1)) / MK_WARPS);
+    const long long nblk = N >> 3;
+    c.rb_lo = (int)((nblk * blockIdx.x) / gridDim.x);
+    c.nb = (int)((nblk * (blockIdx.x + 1)) / gridDim.x) - c.rb_lo;
+    const int nk32 = c.K >> 5;
+    c.ks_lo = (nk32 * w.warp) / MK_WARPS;
+    c.ks_len = (nk32 * (w.warp + 1)) / MK_WARPS - c.ks_lo;
     return c;
 }
 
@@ -464,15 +460,13 @@ template <int NB>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p) {
     extern __shared__ __align__(16) uint8_t mk_smem[];
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(mk_smem);  // [NB][Kmax]
+    float* s_gpart = reinterpret_cast<float*>(mk_smem + (size_t)NB * (p.h > p.I ? p.h : p.I) * 2);  // [16][MAXNB][NB][8]
     __shared__ float s_red[MK_WARPS][NB];
     __shared__ float s_rstd[NB];
     __shared__ float s_av[MK_WARPS];
     __shared__ int s_ai[MK_WARPS];
     __shared__ float s_part[MK_WARPS][MK_D + 2];
     __shared__ int s_flag;
-    __shared__ float s_sums[MK_MAXROWS][NB];
-    __shared__ float s_pa[MK_WARPS][NB];
-    __shared__ float s_pb[MK_WARPS][NB];
 
     WarpId w;
     w.tid = threadIdx.x; w.lane = w.tid & 31; w.warp = w.tid >> 5;
@@ -481,7 +475,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     const int B = p.B;
 
     uint4 bufA[MK_UB], bufB[MK_UB];
-    float acc[NB];
+    float acc[4];
 
     // ---------------- phase "-1": x = embed_tokens[tok]; layer-0 QKV weights already in flight ----------------
     GemvCtx cur = mk_phase_ctx(p, 0, w);
@@ -505,22 +499,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             // the first step's weights were issued (into bufA) before the preceding barrier
             mk_prologue<NB>(mk_phase_io(p, ph), cur.K, B, p.eps, w, xs, s_red, s_rstd);
             RowState st;
-            st.row = cur.u_lo / cur.nchunks;
-            st.chunk = cur.u_lo - st.row * cur.nchunks;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-            const int n_batches = (cur.u_hi - cur.u_lo + MK_UB - 1) / MK_UB;
+            st.rb = 0;
+            st.kk = 0;
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+            const int n_batches = (cur.nb * cur.ks_len + MK_UB - 1) / MK_UB;
             // batches 0 and 1 were issued (bufA, bufB) before the preceding barrier
 #pragma unroll 1
             for (int bt = 0; bt < n_batches; bt += 2) {
-                mk_compute<NB>(cur, bt, w, bufA, xs, st, acc, s_sums, s_pa, s_pb);
+                mk_compute<NB>(cur, bt, B, w, bufA, xs, st, acc, s_gpart);
                 mk_issue(cur, bt + 2, w, bufA);
-                mk_compute<NB>(cur, bt + 1, w, bufB, xs, st, acc, s_sums, s_pa, s_pb);
+                mk_compute<NB>(cur, bt + 1, B, w, bufB, xs, st, acc, s_gpart);
                 mk_issue(cur, bt + 3, w, bufB);
             }
-            if (st.chunk != 0) mk_flush<NB>(cur, w, st, false, acc, s_sums, s_pa, s_pb);  // row cut by the warp boundary
             __syncthreads();
-            mk_epilogue<NB>(p, ph, cur, B, w, s_sums, s_pa, s_pb);
+            mk_epilogue<NB>(p, ph, cur, B, w, s_gpart);
         }
         // prefetch the next GEMV phase's first weights across the barrier (weights don't depend on activations)
         int nxt = ph + 1;
@@ -530,7 +522,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             mk_issue(cur, 0, w, bufA);
             mk_issue(cur, 1, w, bufB);
         } else {
-            cur.u_lo = cur.u_hi = 0;
+            cur.nb = 0;
             mk_issue(cur, 0, w, bufA);  // defines the buffers (zeros): nothing is carried across the attention phase
             mk_issue(cur, 1, w, bufB);
         }
@@ -586,13 +578,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 
 }  // namespace
 
-// dynamic activation tile [NB][max(h, I)] bf16 + ~(MK_MAXROWS + 2*16 + 16 + 1) * NB floats of static tables
+// dynamic smem: activation tile [NB][max(h, I)] bf16 + K-slice partial sums [16][MK_MAXNB][NB][8] fp32
+static size_t mega_smem_bytes(int NB, int h, int I) {
+    return (size_t)NB * (h > I ? h : I) * 2 + (size_t)MK_WARPS * MK_MAXNB * NB * 8 * 4;
+}
 bool decode_mega_fits(int B, int h, int I) {
     if (B < 1 || B > 8) return false;
     const int NB = B == 1 ? 1 : (B == 2 ? 2 : (B <= 4 ? 4 : 8));
-    const size_t dyn = (size_t)NB * (h > I ? h : I) * 2;
-    const size_t stat = (size_t)(MK_MAXROWS + 3 * MK_WARPS + 1) * NB * 4 + MK_WARPS * (MK_D + 2) * 4 + 512;
-    return dyn + stat <= 227 * 1024;
+    const size_t stat = (size_t)(MK_WARPS + 1) * NB * 4 + MK_WARPS * (MK_D + 2) * 4 + 1024;
+    return mega_smem_bytes(NB, h, I) + stat <= 227 * 1024;
 }
 
 int decode_mega(const MegaParams& p, cudaStream_t stream) {
@@ -602,12 +596,12 @@ int decode_mega(const MegaParams& p, cudaStream_t stream) {
     {
         const int grid = num_sms();
         const int nmax = p.V > 3 * p.h ? (p.V > 2 * p.I ? p.V : 2 * p.I) : (3 * p.h > 2 * p.I ? 3 * p.h : 2 * p.I);
-        B2_CHECK_ARG(2 * ((nmax / 2 + grid - 1) / grid) + 2 <= MK_MAXROWS,
-                     "decode_mega: %d output rows per CTA exceed the shared-memory row table", nmax / grid);
+        B2_CHECK_ARG((nmax / 8 + grid - 1) / grid + 1 <= MK_MAXNB && p.V % 8 == 0,
+                     "decode_mega: %d output rows per CTA exceed the shared-memory block table", nmax / grid);
     }
     const int NB = p.B == 1 ? 1 : (p.B == 2 ? 2 : (p.B <= 4 ? 4 : 8));
     const int kmax = p.h > p.I ? p.h : p.I;
-    const size_t smem = (size_t)NB * kmax * 2;
+    const size_t smem = mega_smem_bytes(NB, p.h, p.I);
     B2_CHECK_ARG(decode_mega_fits(p.B, p.h, p.I), "decode_mega: activations do not fit shared memory (B=%d K=%d)",
                  p.B, kmax);
     void* fn = nullptr;
