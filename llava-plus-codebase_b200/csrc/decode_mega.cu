@@ -30,25 +30,20 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 
-// sense-reversing grid barrier (all CTAs co-resident: cooperative launch, grid = #SMs)
-__device__ __forceinline__ void grid_sync(unsigned int* count, unsigned int* gen, unsigned int nblocks) {
+// Grid barrier (all CTAs co-resident: cooperative launch, grid = #SMs). One monotonically increasing counter:
+// every CTA does a fire-and-forget red.release (+1) and polls with ld.acquire until the counter reaches the
+// target the host-provided launch sequence number implies — one L2 round trip on the critical path instead of
+// the four (load generation, fence, atomic, poll) of a sense-reversing barrier. Signed difference compare
+// survives 32-bit wrap-around.
+__device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int g;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(gen) : "memory");
-        __threadfence();
-        if (atomicAdd(count, 1u) == nblocks - 1) {
-            *reinterpret_cast<volatile unsigned int*>(count) = 0u;
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gen) : "memory");
-        } else {
-            unsigned int cur;
-            unsigned int spins = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(gen) : "memory");
-                if (++spins > (1u << 26)) asm volatile("trap;");  // protocol bug -> CUDA error, not a hang
-            } while (cur == g);
-        }
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned int cur, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(counter) : "memory");
+            if (++spins > (1u << 26)) asm volatile("trap;");  // protocol bug -> CUDA error, not a hang
+        } while ((int)(cur - target) < 0);
     }
     __syncthreads();
 }
@@ -260,7 +255,8 @@ __device__ __forceinline__ void mk_epilogue(const MegaParams& p, int ph, const G
 // pairs one after the other. Inside a CTA the 16 warps split the key range (half-warp per 256 B K/V row,
 // online softmax in registers) and merge through shared memory, so no long serial merge sits on the critical path.
 __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLayer& Lw, const WarpId& w,
-                                             float (*s_part)[MK_D + 2], int* s_flag) {
+                                             float (*s_part)[MK_D + 2], int* s_flag, const float* s_cos,
+                                             const float* s_sin) {
     const int h = p.h, H = p.H;
     const int pairs = p.B * H;
     const int grid = gridDim.x;
@@ -292,11 +288,8 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
             const float sign = (c < 8) ? -1.f : 1.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int i = ((c & 7) * 8 + e);  // frequency index 0..63
-                const float inv_freq = exp2f(-(2.0f * i / MK_D) * log2f(p.theta));
-                float sv, cv;
-                sincosf(pos * inv_freq, &sv, &cv);
-                const float cbf = round_bf16(cv), sbf = round_bf16(sv);
+                const int i = ((c & 7) * 8 + e);  // frequency index 0..63; cos/sin(pos_b * inv_freq_i) tabulated once per step
+                const float cbf = s_cos[b * 64 + i], sbf = s_sin[b * 64 + i];
                 qreg[e] = round_bf16(round_bf16(qa[e] * cbf) + round_bf16(sign * qb[e] * sbf));
                 knew[e] = round_bf16(round_bf16(ka[e] * cbf) + round_bf16(sign * kb[e] * sbf));
             }
@@ -467,6 +460,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     __shared__ int s_ai[MK_WARPS];
     __shared__ float s_part[MK_WARPS][MK_D + 2];
     __shared__ int s_flag;
+    __shared__ float s_cos[NB * 64], s_sin[NB * 64];  // RoPE table of this step (HF: cos/sin cast to bf16)
 
     WarpId w;
     w.tid = threadIdx.x; w.lane = w.tid & 31; w.warp = w.tid >> 5;
@@ -481,6 +475,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     GemvCtx cur = mk_phase_ctx(p, 0, w);
     mk_issue(cur, 0, w, bufA);
     mk_issue(cur, 1, w, bufB);
+    for (int i = w.tid; i < B * 64; i += MK_THREADS) {
+        const int b = i >> 6, f = i & 63;
+        const float inv_freq = exp2f(-(2.0f * f / MK_D) * log2f(p.theta));
+        float sv, cv;
+        sincosf((float)p.cur_len[b] * inv_freq, &sv, &cv);
+        s_cos[i] = round_bf16(cv);
+        s_sin[i] = round_bf16(sv);
+    }
     if (blockIdx.x < B) {
         int t = p.tok[blockIdx.x];
         t = t < 0 ? 0 : (t >= p.V ? p.V - 1 : t);
@@ -488,16 +490,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
         uint4* dst = reinterpret_cast<uint4*>(p.x + (size_t)blockIdx.x * p.h);
         for (int i = w.tid; i < p.h / 8; i += MK_THREADS) dst[i] = src[i];
     }
-    grid_sync(p.bar_count, p.bar_gen, gridDim.x);
+    unsigned int bar_target = p.bar_base + gridDim.x;
+    grid_sync(p.bar_count, bar_target);
 
     const int n_phases = 5 * p.L + 1;
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && w.tid == 0;
 #pragma unroll 1
     for (int ph = 0; ph < n_phases; ++ph) {
+        if (tracing) p.trace[ph * 4 + 0] = clock64();
         if (ph % 5 == 1 && ph < 5 * p.L) {
-            mk_attention(p, p.layers[ph / 5], w, s_part, &s_flag);
+            mk_attention(p, p.layers[ph / 5], w, s_part, &s_flag, s_cos, s_sin);
         } else {
             // the first step's weights were issued (into bufA) before the preceding barrier
             mk_prologue<NB>(mk_phase_io(p, ph), cur.K, B, p.eps, w, xs, s_red, s_rstd);
+            if (tracing) p.trace[ph * 4 + 1] = clock64();
             RowState st;
             st.rb = 0;
             st.kk = 0;
@@ -512,6 +518,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                 mk_issue(cur, bt + 3, w, bufB);
             }
             __syncthreads();
+            if (tracing) p.trace[ph * 4 + 2] = clock64();
             mk_epilogue<NB>(p, ph, cur, B, w, s_gpart);
         }
         // prefetch the next GEMV phase's first weights across the barrier (weights don't depend on activations)
@@ -526,8 +533,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             mk_issue(cur, 0, w, bufA);  // defines the buffers (zeros): nothing is carried across the attention phase
             mk_issue(cur, 1, w, bufB);
         }
-        grid_sync(p.bar_count, p.bar_gen, gridDim.x);
+        if (tracing) p.trace[ph * 4 + 3] = clock64();
+        bar_target += gridDim.x;
+        grid_sync(p.bar_count, bar_target);
     }
+    if (tracing) p.trace[n_phases * 4] = clock64();
 
     // ---------------- greedy argmax (first occurrence), token store, counters ----------------
     if (blockIdx.x < B) {

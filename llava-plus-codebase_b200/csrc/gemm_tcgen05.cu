@@ -32,7 +32,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quadrant)
+constexpr int kNumEpiWarps = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
 template <int BN>
@@ -53,11 +54,11 @@ struct EpiParams {
     int out_fp32;
 };
 
-__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float act_gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 template <int BN, int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -106,7 +107,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], kNumEpiWarps);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -169,8 +170,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
         }
     } else {
-        // ===================== epilogue warps 2..5 =====================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        // ===================== epilogue warps 2..9 =====================
+        const int q = warp & 3;            // TMEM lane quadrant this warp may access (warp_id % 4)
+        const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the tile's columns
         int local = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
             int m_blk, n_blk;
@@ -188,9 +190,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 // for the same 64 output channels. out is [M, N/2].
                 static_assert(BN % 128 == 0, "swiglu needs BN multiple of 128");
 #pragma unroll 1
-                for (int g = 0; g < BN / 128; ++g) {
-#pragma unroll 1
-                    for (int j = 0; j < 2; ++j) {
+                for (int it = half * (BN / 128); it < (half + 1) * (BN / 128); ++it) {
+                    {
+                        const int g = it >> 1, j = it & 1;
                         uint32_t vg[32], vu[32];
                         __syncwarp();
                         tmem_ld_32x32(taddr_row + g * 128 + j * 32, vg);
@@ -219,7 +221,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                     uint32_t v[32];
                     __syncwarp();
                     tmem_ld_32x32(taddr_row + c * 32, v);
@@ -377,10 +379,14 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                      ((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ld_res % 8) == 0),
                  "gemm: residual must be 16B aligned with ld_res %% 8 == 0");
 
-    // Tile-N choice: keep >= ~1 wave of tiles when the problem is small (prefill at M=704, ViT at B=1).
+    // Tile-N choice (measured, profiles/r1b_gemm_sweep.json): BN=256 feeds the tensor pipe best (96 B/clk of smem
+    // operand traffic vs 128 B/clk at BN=128, the smem limit) and wins whenever it still yields >= ~0.55 waves of
+    // tiles; smaller tiles only for problems that would otherwise leave most SMs idle.
     const int num_m = (g.M + BM - 1) / BM;
-    int bn = 128;
-    if (g.act != ACT_SWIGLU && num_m * ((g.N + 127) / 128) < num_sms()) bn = 64;
+    const int want = (num_sms() * 55) / 100;
+    int bn = 64;
+    if (num_m * ((g.N + 255) / 256) >= want) bn = 256;
+    else if (num_m * ((g.N + 127) / 128) >= want) bn = 128;
     if (g.bn_override == 64 || g.bn_override == 128 || g.bn_override == 256) bn = g.bn_override;
     if (g.act == ACT_SWIGLU && bn < 128) bn = 128;
 

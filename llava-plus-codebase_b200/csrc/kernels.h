@@ -105,8 +105,10 @@ struct MegaParams {
     float* logits = nullptr;
     float* attn_partial = nullptr;      // [B*H*nsplit*(128+2)]
     int32_t* attn_counters = nullptr;   // [B*H], zero-initialised, self-resetting
-    unsigned int *bar_count = nullptr, *bar_gen = nullptr, *done_count = nullptr;  // zero-initialised
+    unsigned int *bar_count = nullptr, *done_count = nullptr;  // zero-initialised
+    unsigned int bar_base = 0;  // barrier-counter value before this launch = launches so far * (5L+2) * grid
     float eps = 1e-5f, theta = 10000.f, scale_log2 = 1.f;
+    long long* trace = nullptr;  // optional [n_phases+2][4] SM-clock timestamps of CTA 0 (B2_MEGA_TRACE=1)
 };
 // one launch = embed -> all layers -> lm_head -> argmax -> token store; cur_len/step_counter advance on device
 int decode_mega(const MegaParams& p, cudaStream_t stream);

@@ -100,6 +100,7 @@ struct b2_kv {
     int graph_B = 0;
     // stream capture is illegal on the legacy default stream (torch's default current stream): decode steps
     // run on this library-owned stream, ordered against the caller's stream with events
+    unsigned int mega_bar_base = 0;  // value of the grid-barrier counter before the next megakernel launch
     DevBuf mega_layers, mega_sync;  // MegaLayer[L] table and {bar_count, bar_gen, done_count}
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -440,9 +441,37 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     p.logits = m->logits.as<float>();
     p.attn_partial = kv->attn_partial.as<float>(); p.attn_counters = kv->attn_counters.as<int32_t>();
     unsigned int* sync = kv->mega_sync.as<unsigned int>();
-    p.bar_count = sync; p.bar_gen = sync + 1; p.done_count = sync + 2;
+    p.bar_count = sync; p.done_count = sync + 2;
+    p.bar_base = kv->mega_bar_base;
+    kv->mega_bar_base += (unsigned int)(5 * d.layers + 2) * (unsigned int)num_sms();
     p.eps = d.rms_eps; p.theta = d.rope_theta;
     p.scale_log2 = (1.0f / sqrtf((float)m->hd)) * 1.4426950408889634f;
+    static int trace_mode = -1;
+    if (trace_mode < 0) { const char* e = getenv("B2_MEGA_TRACE"); trace_mode = (e && e[0] == '1') ? 1 : 0; }
+    if (trace_mode == 1) {
+        // debug: per-phase SM-clock timestamps of CTA 0 for one step, dumped to gpurun_out/mega_trace.txt
+        static int steps_seen = 0;
+        if (++steps_seen == 40) {
+            const int n = (5 * d.layers + 2) * 4;
+            DevBuf tb;
+            B2_TRY(tb.alloc((size_t)n * 8));
+            cudaMemset(tb.p, 0, (size_t)n * 8);
+            p.trace = tb.as<long long>();
+            int r = decode_mega(p, st);
+            cudaStreamSynchronize(st);
+            std::vector<long long> host(n);
+            cudaMemcpy(host.data(), tb.p, (size_t)n * 8, cudaMemcpyDeviceToHost);
+            FILE* f = fopen("gpurun_out/mega_trace.txt", "w");
+            if (f) {
+                for (int ph = 0; ph <= 5 * d.layers; ++ph)
+                    fprintf(f, "%d %lld %lld %lld %lld %lld\n", ph, host[ph * 4], host[ph * 4 + 1], host[ph * 4 + 2],
+                            host[ph * 4 + 3], host[(ph + 1) * 4]);
+                fclose(f);
+            }
+            tb.free();
+            return r;
+        }
+    }
     return decode_mega(p, st);
 }
 
