@@ -76,7 +76,8 @@ struct PhaseIO {
 };
 
 struct WarpId { int tid, lane, warp, gw, total_warps; };
-__device__ __forceinline__ PhaseIO mk_phase_io(const MegaParams& p, int ph);
+constexpr int MK_MAXL = 48;  // decoder layers whose weight-pointer table is cached in shared memory
+__device__ __forceinline__ PhaseIO mk_phase_io(const MegaParams& p, const MegaLayer* layers, int ph);
 
 constexpr int MK_UB = 8;      // units (16 B loads per lane) per pipeline batch
 constexpr int MK_MAXNB = 32;  // max 8-row blocks per CTA per phase (host-checked)
@@ -223,9 +224,9 @@ __device__ __forceinline__ float mk_row_value(const float* s_part, int nk32, int
 
 // after the streaming loop: reduce the 16 K-slices, apply the epilogue, coalesced global writes
 template <int NB>
-__device__ __forceinline__ void mk_epilogue(const MegaParams& p, int ph, const GemvCtx& c, int B, const WarpId& w,
-                                            const float* s_part) {
-    const PhaseIO io = mk_phase_io(p, ph);
+__device__ __forceinline__ void mk_epilogue(const MegaParams& p, const MegaLayer* layers, int ph, const GemvCtx& c,
+                                            int B, const WarpId& w, const float* s_part) {
+    const PhaseIO io = mk_phase_io(p, layers, ph);
     if (c.act == ACT_SWIGLU) {
         const int nch = c.nb * 4;
         for (int idx = w.tid; idx < nch * B; idx += MK_THREADS) {
@@ -419,27 +420,27 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
 }
 
 // phase k of layer l (k: 0 = QKV, 1 = attention, 2 = o_proj, 3 = gate/up, 4 = down); index 5L = lm_head
-__device__ __forceinline__ PhaseIO mk_phase_io(const MegaParams& p, int ph) {
+__device__ __forceinline__ PhaseIO mk_phase_io(const MegaParams& p, const MegaLayer* layers, int ph) {
     PhaseIO c;
     const int l = ph / 5, k = ph % 5;
     c.gamma = nullptr; c.residual = nullptr; c.out_fp32 = 0;
     if (l >= p.L) { c.xin = p.x; c.gamma = p.final_norm; c.out = p.logits; c.ld_out = p.V; c.out_fp32 = 1; }
-    else if (k <= 1) { c.xin = p.x; c.gamma = p.layers[l].ln1; c.out = p.qkv; c.ld_out = 3 * p.h; }
+    else if (k <= 1) { c.xin = p.x; c.gamma = layers[l].ln1; c.out = p.qkv; c.ld_out = 3 * p.h; }
     else if (k == 2) { c.xin = p.attn; c.residual = p.x; c.out = p.x; c.ld_out = p.h; }
-    else if (k == 3) { c.xin = p.x; c.gamma = p.layers[l].ln2; c.out = p.act; c.ld_out = p.I; }
+    else if (k == 3) { c.xin = p.x; c.gamma = layers[l].ln2; c.out = p.act; c.ld_out = p.I; }
     else { c.xin = p.act; c.residual = p.x; c.out = p.x; c.ld_out = p.h; }
     return c;
 }
-__device__ __forceinline__ GemvCtx mk_phase_ctx(const MegaParams& p, int ph, const WarpId& w) {
+__device__ __forceinline__ GemvCtx mk_phase_ctx(const MegaParams& p, const MegaLayer* layers, int ph, const WarpId& w) {
     GemvCtx c;
     const int l = ph / 5, k = ph % 5;
     int N;
     c.act = ACT_NONE;
     if (l >= p.L) { c.W = p.lm_head; N = p.V; c.K = p.h; }
-    else if (k <= 1) { c.W = p.layers[l].wqkv; N = 3 * p.h; c.K = p.h; }
-    else if (k == 2) { c.W = p.layers[l].wo; N = p.h; c.K = p.h; }
-    else if (k == 3) { c.W = p.layers[l].wgu; N = 2 * p.I; c.K = p.h; c.act = ACT_SWIGLU; }
-    else { c.W = p.layers[l].wd; N = p.h; c.K = p.I; }
+    else if (k <= 1) { c.W = layers[l].wqkv; N = 3 * p.h; c.K = p.h; }
+    else if (k == 2) { c.W = layers[l].wo; N = p.h; c.K = p.h; }
+    else if (k == 3) { c.W = layers[l].wgu; N = 2 * p.I; c.K = p.h; c.act = ACT_SWIGLU; }
+    else { c.W = layers[l].wd; N = p.h; c.K = p.I; }
     const long long nblk = N >> 3;
     c.rb_lo = (int)((nblk * blockIdx.x) / gridDim.x);
     c.nb = (int)((nblk * (blockIdx.x + 1)) / gridDim.x) - c.rb_lo;
@@ -460,7 +461,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     __shared__ int s_ai[MK_WARPS];
     __shared__ float s_part[MK_WARPS][MK_D + 2];
     __shared__ int s_flag;
-    __shared__ float s_cos[NB * 64], s_sin[NB * 64];  // RoPE table of this step (HF: cos/sin cast to bf16)
+    __shared__ float s_cos[NB * 64], s_sin[NB * 64];
+    __shared__ MegaLayer s_layers[MK_MAXL];  // weight-pointer table: no dependent global load per phase  // RoPE table of this step (HF: cos/sin cast to bf16)
 
     WarpId w;
     w.tid = threadIdx.x; w.lane = w.tid & 31; w.warp = w.tid >> 5;
@@ -471,8 +473,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     uint4 bufA[MK_UB], bufB[MK_UB];
     float acc[4];
 
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.layers);
+        uint4* dst = reinterpret_cast<uint4*>(s_layers);
+        for (int i = w.tid; i < p.L * (int)(sizeof(MegaLayer) / 16); i += MK_THREADS) dst[i] = src[i];
+        __syncthreads();
+    }
+
     // ---------------- phase "-1": x = embed_tokens[tok]; layer-0 QKV weights already in flight ----------------
-    GemvCtx cur = mk_phase_ctx(p, 0, w);
+    GemvCtx cur = mk_phase_ctx(p, s_layers, 0, w);
     mk_issue(cur, 0, w, bufA);
     mk_issue(cur, 1, w, bufB);
     for (int i = w.tid; i < B * 64; i += MK_THREADS) {
@@ -499,10 +508,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     for (int ph = 0; ph < n_phases; ++ph) {
         if (tracing) p.trace[ph * 4 + 0] = clock64();
         if (ph % 5 == 1 && ph < 5 * p.L) {
-            mk_attention(p, p.layers[ph / 5], w, s_part, &s_flag, s_cos, s_sin);
+            mk_attention(p, s_layers[ph / 5], w, s_part, &s_flag, s_cos, s_sin);
         } else {
             // the first step's weights were issued (into bufA) before the preceding barrier
-            mk_prologue<NB>(mk_phase_io(p, ph), cur.K, B, p.eps, w, xs, s_red, s_rstd);
+            mk_prologue<NB>(mk_phase_io(p, s_layers, ph), cur.K, B, p.eps, w, xs, s_red, s_rstd);
             if (tracing) p.trace[ph * 4 + 1] = clock64();
             RowState st;
             st.rb = 0;
@@ -519,13 +528,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             }
             __syncthreads();
             if (tracing) p.trace[ph * 4 + 2] = clock64();
-            mk_epilogue<NB>(p, ph, cur, B, w, s_gpart);
+            mk_epilogue<NB>(p, s_layers, ph, cur, B, w, s_gpart);
         }
         // prefetch the next GEMV phase's first weights across the barrier (weights don't depend on activations)
         int nxt = ph + 1;
         if (nxt % 5 == 1 && nxt < 5 * p.L) nxt = -1;  // attention follows: no weights to prefetch yet
         if (nxt >= 0 && nxt < n_phases) {
-            cur = mk_phase_ctx(p, nxt, w);
+            cur = mk_phase_ctx(p, s_layers, nxt, w);
             mk_issue(cur, 0, w, bufA);
             mk_issue(cur, 1, w, bufB);
         } else {
@@ -595,12 +604,13 @@ static size_t mega_smem_bytes(int NB, int h, int I) {
 bool decode_mega_fits(int B, int h, int I) {
     if (B < 1 || B > 8) return false;
     const int NB = B == 1 ? 1 : (B == 2 ? 2 : (B <= 4 ? 4 : 8));
-    const size_t stat = (size_t)(MK_WARPS + 1) * NB * 4 + MK_WARPS * (MK_D + 2) * 4 + 1024;
+    const size_t stat = (size_t)(MK_WARPS + 1) * NB * 4 + MK_WARPS * (MK_D + 2) * 4 + NB * 512 + MK_MAXL * sizeof(MegaLayer) + 1024;
     return mega_smem_bytes(NB, h, I) + stat <= 227 * 1024;
 }
 
 int decode_mega(const MegaParams& p, cudaStream_t stream) {
     B2_CHECK_ARG(p.B >= 1 && p.B <= 8, "decode_mega: batch must be 1..8");
+    B2_CHECK_ARG(p.L <= MK_MAXL, "decode_mega: %d layers exceed the shared layer table (%d)", p.L, MK_MAXL);
     B2_CHECK_ARG(p.h % 256 == 0 && p.I % 256 == 0 && p.V % 2 == 0 && p.h / p.H == MK_D,
                  "decode_mega: unsupported dims h=%d I=%d V=%d H=%d", p.h, p.I, p.V, p.H);
     {

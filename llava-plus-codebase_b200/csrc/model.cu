@@ -418,7 +418,7 @@ int join_stream(b2_kv* kv, cudaStream_t st, cudaStream_t run) {
 
 // run one step, through the cached CUDA graph when possible
 bool use_mega(const b2_model* m, int B) {
-    if (!decode_mega_fits(B, m->d.hidden, m->d.inter)) return false;
+    if (!decode_mega_fits(B, m->d.hidden, m->d.inter) || m->d.layers > 48) return false;
     static int flag = -1;
     if (flag < 0) {
         const char* e = getenv("B2_DECODE_MEGA");
