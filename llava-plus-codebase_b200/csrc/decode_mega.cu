@@ -29,7 +29,8 @@ namespace {
 
 constexpr int MK_CONS_WARPS = 16;
 constexpr int MK_CONS = MK_CONS_WARPS * 32;   // 512 consumer threads
-constexpr int MK_THREADS = MK_CONS + 32;      // + 1 producer warp
+constexpr int MK_PROD_WARPS = 4;              // TMA issue is per-thread work: tiles are dealt round-robin to 4 producer warps
+constexpr int MK_THREADS = MK_CONS + 32 * MK_PROD_WARPS;
 constexpr int MK_D = 128;
 constexpr int MK_U = 4;                       // keys per half-warp per attention iteration
 constexpr int MK_KT = 1024;                   // K elements per weight tile (8 rows x 1024 bf16 = 16 KB)
@@ -39,6 +40,7 @@ constexpr int MK_TILE_BYTES = 8 * MK_ROW_STRIDE;
 constexpr int MK_MAXNB = 32;                  // max 8-row blocks per CTA per phase (host-checked)
 constexpr int MK_MAXL = 48;                   // decoder layers whose weight-pointer table is cached in smem
 constexpr int MK_MAX_STAGES = 12;
+constexpr int MK_L2_AHEAD = 16;               // tiles (x 16 KB x 148 CTAs = 38 MB) prefetched into L2 beyond the ring; multiple of MK_PROD_WARPS
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
@@ -396,6 +398,40 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
     }
 }
 
+// position in the CTA's tile sequence over all GEMV phases (phase -> 8-row block -> K tile)
+struct TileCursor {
+    GemvCtx c;
+    int ph, rb, kc;
+    uint32_t tile;
+    bool valid;
+};
+__device__ __forceinline__ void cursor_seek(TileCursor& t, const MegaParams& p, const MegaLayer* layers, int n_phases) {
+    // move to the first phase at or after t.ph that is a GEMV phase with work for this CTA
+    while (t.ph < n_phases) {
+        if (!mk_is_attention(p, t.ph)) {
+            t.c = mk_phase_ctx(p, layers, t.ph);
+            if (t.c.nb > 0) { t.rb = 0; t.kc = 0; t.valid = true; return; }
+        }
+        ++t.ph;
+    }
+    t.valid = false;
+}
+__device__ __forceinline__ void cursor_begin(TileCursor& t, const MegaParams& p, const MegaLayer* layers, int n_phases) {
+    t.ph = 0; t.tile = 0; t.rb = 0; t.kc = 0;
+    cursor_seek(t, p, layers, n_phases);
+}
+__device__ __forceinline__ void cursor_next(TileCursor& t, const MegaParams& p, const MegaLayer* layers, int n_phases) {
+    ++t.tile;
+    if (++t.kc < t.c.nchunk) return;
+    t.kc = 0;
+    if (++t.rb < t.c.nb) return;
+    ++t.ph;
+    cursor_seek(t, p, layers, n_phases);
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 template <int NB>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p, int n_stages) {
     extern __shared__ __align__(128) uint8_t mk_smem[];
@@ -418,7 +454,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
     const int B = p.B;
     const int n_phases = 5 * p.L + 1;
 
-    // ---- one-time setup (all 17 warps) ----
+    // ---- one-time setup (all warps) ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.layers);
         uint4* dst = reinterpret_cast<uint4*>(s_layers);
@@ -433,28 +469,46 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
         __syncthreads();
     }
 
-    if (warp == MK_CONS_WARPS) {
-        // =========================== PRODUCER: stream every phase's weight tiles, in order ===========================
-        uint32_t tile = 0;
-        for (int ph = 0; ph < n_phases; ++ph) {
-            if (mk_is_attention(p, ph)) continue;
-            const GemvCtx c = mk_phase_ctx(p, s_layers, ph);
-            for (int rb = 0; rb < c.nb; ++rb) {
-                const __nv_bfloat16* row = c.W + (size_t)mk_phys_row(c.act, c.rb_lo + rb, lane & 7) * c.K;
-                for (int kc = 0; kc < c.nchunk; ++kc, ++tile) {
-                    const uint32_t stage = tile % (uint32_t)n_stages;
-                    const uint32_t parity = (tile / (uint32_t)n_stages) & 1u;
-                    const uint32_t row_bytes = (uint32_t)min(MK_KT, c.K - kc * MK_KT) * 2u;
-                    if (lane == 0) {
-                        mbar_wait(&empty_bar[stage], parity ^ 1u);  // slot drained by all consumer warps
-                        mbar_arrive_expect_tx(&full_bar[stage], 8u * row_bytes);
-                    }
-                    __syncwarp();
-                    if (lane < 8)
-                        bulk_g2s(ring + (size_t)stage * MK_TILE_BYTES + (size_t)lane * MK_ROW_STRIDE,
-                                 row + (size_t)kc * MK_KT, row_bytes, &full_bar[stage]);
+    if (warp >= MK_CONS_WARPS) {
+        // =========================== PRODUCERS: stream every phase's weight tiles, in order ===========================
+        // Two cursors walk the same tile sequence: `cp` feeds the shared-memory ring with TMA bulk copies (throttled
+        // by free ring slots), `pf` runs MK_L2_AHEAD tiles ahead of it issuing bulk L2 prefetches (no smem needed), so
+        // while the consumers sit in a barrier/prologue and the ring is full, HBM keeps streaming the next phase's
+        // weights into the 126 MB L2 and the ring refills from L2 afterwards.
+        const uint32_t pw = (uint32_t)(warp - MK_CONS_WARPS);
+        TileCursor cp, pf;
+        cursor_begin(cp, p, s_layers, n_phases);
+        cursor_begin(pf, p, s_layers, n_phases);
+        for (int i = 0; i < MK_L2_AHEAD && pf.valid; ++i) {
+            if (pf.tile % (uint32_t)MK_PROD_WARPS == pw && lane < 8) {
+                const uint32_t row_bytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
+                bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
+                                     (size_t)pf.kc * MK_KT, row_bytes);
+            }
+            cursor_next(pf, p, s_layers, n_phases);
+        }
+        while (cp.valid) {
+            if (cp.tile % (uint32_t)MK_PROD_WARPS == pw) {
+                const uint32_t stage = cp.tile % (uint32_t)n_stages;
+                const uint32_t parity = (cp.tile / (uint32_t)n_stages) & 1u;
+                const uint32_t row_bytes = (uint32_t)min(MK_KT, cp.c.K - cp.kc * MK_KT) * 2u;
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[stage], parity ^ 1u);  // slot drained by all consumer warps
+                    mbar_arrive_expect_tx(&full_bar[stage], 8u * row_bytes);
+                }
+                __syncwarp();
+                if (lane < 8)
+                    bulk_g2s(ring + (size_t)stage * MK_TILE_BYTES + (size_t)lane * MK_ROW_STRIDE,
+                             cp.c.W + (size_t)mk_phys_row(cp.c.act, cp.c.rb_lo + cp.rb, lane) * cp.c.K +
+                                 (size_t)cp.kc * MK_KT, row_bytes, &full_bar[stage]);
+                if (pf.valid && lane < 8) {  // pf.tile == cp.tile + MK_L2_AHEAD: same residue mod MK_PROD_WARPS
+                    const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
+                    bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
+                                         (size_t)pf.kc * MK_KT, pbytes);
                 }
             }
+            cursor_next(cp, p, s_layers, n_phases);
+            if (pf.valid) cursor_next(pf, p, s_layers, n_phases);
         }
         return;
     }
