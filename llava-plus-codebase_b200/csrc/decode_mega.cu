@@ -33,14 +33,16 @@ constexpr int MK_PROD_WARPS = 4;              // TMA issue is per-thread work: t
 constexpr int MK_THREADS = MK_CONS + 32 * MK_PROD_WARPS;
 constexpr int MK_D = 128;
 constexpr int MK_U = 4;                       // keys per half-warp per attention iteration
-constexpr int MK_KT = 1024;                   // K elements per weight tile (8 rows x 1024 bf16 = 16 KB)
+constexpr int MK_KT = 2048;                   // K elements per weight tile (8 rows x 2048 bf16 = 32 KB): per-tile mbarrier
+                                              // wait/arrive overhead of the 16 consumer warps is amortised over 4 k32 slices each
 constexpr int MK_ROW_PAD = 64;                // bytes of padding per tile row -> conflict-free 16 B fragment loads
 constexpr int MK_ROW_STRIDE = MK_KT * 2 + MK_ROW_PAD;
 constexpr int MK_TILE_BYTES = 8 * MK_ROW_STRIDE;
 constexpr int MK_MAXNB = 32;                  // max 8-row blocks per CTA per phase (host-checked)
 constexpr int MK_MAXL = 48;                   // decoder layers whose weight-pointer table is cached in smem
 constexpr int MK_MAX_STAGES = 12;
-constexpr int MK_L2_AHEAD = 16;               // tiles (x 16 KB x 148 CTAs = 38 MB) prefetched into L2 beyond the ring; multiple of MK_PROD_WARPS
+constexpr int MK_L2_AHEAD = 0;                // tiles prefetched into L2 beyond the ring (multiple of MK_PROD_WARPS). Measured: 16
+                                              // tiles (38 MB chip-wide) made the step 5% SLOWER (extra TMA issue work, no gain) -> off
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
@@ -501,14 +503,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                     bulk_g2s(ring + (size_t)stage * MK_TILE_BYTES + (size_t)lane * MK_ROW_STRIDE,
                              cp.c.W + (size_t)mk_phys_row(cp.c.act, cp.c.rb_lo + cp.rb, lane) * cp.c.K +
                                  (size_t)cp.kc * MK_KT, row_bytes, &full_bar[stage]);
-                if (pf.valid && lane < 8) {  // pf.tile == cp.tile + MK_L2_AHEAD: same residue mod MK_PROD_WARPS
+                if (MK_L2_AHEAD > 0 && pf.valid && lane < 8) {  // pf.tile == cp.tile + MK_L2_AHEAD: same residue mod MK_PROD_WARPS
                     const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
                     bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
                                          (size_t)pf.kc * MK_KT, pbytes);
                 }
             }
             cursor_next(cp, p, s_layers, n_phases);
-            if (pf.valid) cursor_next(pf, p, s_layers, n_phases);
+            if (MK_L2_AHEAD > 0 && pf.valid) cursor_next(pf, p, s_layers, n_phases);
         }
         return;
     }
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             if (tracing) p.trace[ph * 4 + 1] = clock64();
 #pragma unroll 1
             for (int rb = 0; rb < c.nb; ++rb) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};  // two independent MMA chains
 #pragma unroll 1
                 for (int kc = 0; kc < c.nchunk; ++kc, ++tile) {
                     const uint32_t stage = tile % (uint32_t)n_stages;
@@ -556,13 +558,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                     mbar_wait(&full_bar[stage], parity);  // TMA bytes of this tile have landed
                     const uint8_t* trow = ring + (size_t)stage * MK_TILE_BYTES + (size_t)g * MK_ROW_STRIDE + t4 * 16;
                     const __nv_bfloat16* xrow = xs + (size_t)g * c.K + (size_t)kc * MK_KT + t4 * 8;
-#pragma unroll 2
+#pragma unroll 4
                     for (int k32 = warp; k32 < nk32; k32 += MK_CONS_WARPS) {
                         const uint4 wv = *reinterpret_cast<const uint4*>(trow + k32 * 64);
                         uint4 xv = make_uint4(0, 0, 0, 0);
                         if (g < B) xv = *reinterpret_cast<const uint4*>(xrow + k32 * 32);
                         mk_mma(acc, xv.x, xv.y, wv.x, wv.y);
-                        mk_mma(acc, xv.z, xv.w, wv.z, wv.w);
+                        mk_mma(acc2, xv.z, xv.w, wv.z, wv.w);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done reading the slot
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                 // acc[0], acc[1] = D[batch g][weight rows 2*t4, 2*t4+1] over this warp's K slices
                 if (g < NB)
                     *reinterpret_cast<float2*>(s_gpart + (((size_t)warp * MK_MAXNB + rb) * NB + g) * 8 + t4 * 2) =
-                        make_float2(acc[0], acc[1]);
+                        make_float2(acc[0] + acc2[0], acc[1] + acc2[1]);
             }
             cons_sync();
             if (tracing) p.trace[ph * 4 + 2] = clock64();
