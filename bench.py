@@ -12,9 +12,9 @@ value   : tokens/s = n_gpus * B * (S_prefill + N_decode) / (max-over-ranks devic
           in HBM, CUDA events on the launching stream.
 e2e     : same metric through the public API model.generate(input_ids, images=...) with HOST (pinned) inputs:
           H2D of pixels + ids and D2H of the generated ids inside the timed region.
-roofline: the decode step (one CUDA-graph launch: weight-streaming GEMV kernels + split-KV attention for all
-          layers + lm_head), HBM-bound: algorithmic bytes/step = W + B*(Lc+1)*kv over the measured
-          step time, against MEASURED_PEAKS.json hbm_gbs.
+roofline: the decode step (one launch of the persistent decode megakernel: all layers' weight-streaming GEMV
+          phases + split-KV attention + lm_head + argmax), HBM-bound: algorithmic bytes/step = W + B*(Lc+1)*kv
+           over the measured step time, against MEASURED_PEAKS.json hbm_gbs.
 """
 import argparse
 import json
@@ -388,8 +388,8 @@ def run_ours(args):
                       "encode_tflops": work["encode_flops"] / (t_enc_m * 1e-3) / 1e12},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
-                     "kernel": "decode step = one CUDA-graph launch (gemv_kernel x4 + decode_attn_kernel per layer, "
-                               "lm_head gemv, argmax)",
+                     "kernel": "decode_mega_kernel: one persistent cooperative launch per generated token (all layers' "
+                               "GEMV phases streamed through a TMA smem ring, attention, lm_head, argmax)",
                      "algorithmic_bytes_per_launch": work["decode_bytes_per_step"],
                      "avg_launch_ms": dec_step_ms},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
