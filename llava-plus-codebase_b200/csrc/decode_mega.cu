@@ -77,18 +77,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
-// One GEMV phase as seen by a CTA. Rows are grouped into logical 8-row blocks (SwiGLU: 4 gate rows + the 4 up rows
-// of the same channels) and each block into nchunk K tiles; the (block, tile) sequence of the whole matrix is cut
-// into gridDim.x contiguous, equally long pieces (+-1 tile), so every SM streams the same number of bytes (a
-// block-granular split left 7% of the step on the table: profiles/r1c_mega_phase_trace_v4.txt). A block whose
-// tiles straddle two CTAs is finished by the second one: the first publishes its partial sums through a global
-// scratch + release flag at its epilogue, the second adds them (fixed order -> deterministic).
+// one GEMV phase as seen by a CTA: rows are grouped into logical 8-row blocks (SwiGLU: 4 gate rows + the 4 up
+// rows of the same channels); CTA c owns the contiguous block range [rb_lo, rb_lo + nb)
 struct GemvCtx {
     const __nv_bfloat16* W;
     int K, act;
-    int rb_lo, nb;            // first block touched and number of blocks touched (first/last possibly partially)
-    int nchunk;               // K tiles per block
-    int head_off, tail_end;   // first block starts at tile head_off; last block ends before tile tail_end
+    int rb_lo, nb;
+    int nchunk;  // K tiles per block
 };
 // cold per-phase I/O, recomputed from the phase index where needed (prologue, epilogue)
 struct PhaseIO {
@@ -133,25 +128,9 @@ __device__ __forceinline__ GemvCtx mk_phase_ctx(const MegaParams& p, const MegaL
     else if (k == 3) { c.W = layers[l].wgu; N = 2 * p.I; c.K = p.h; c.act = ACT_SWIGLU; }
     else { c.W = layers[l].wd; N = p.h; c.K = p.I; }
     const long long nblk = N >> 3;
+    c.rb_lo = (int)((nblk * blockIdx.x) / gridDim.x);
+    c.nb = (int)((nblk * (blockIdx.x + 1)) / gridDim.x) - c.rb_lo;
     c.nchunk = (c.K + MK_KT - 1) / MK_KT;
-    const long long T = nblk * c.nchunk;
-    long long t_lo, t_hi;
-    if (T / gridDim.x >= c.nchunk) {  // every CTA gets >= one block's worth of tiles: a block spans <= 2 CTAs
-        t_lo = (T * blockIdx.x) / gridDim.x;
-        t_hi = (T * (blockIdx.x + 1)) / gridDim.x;
-    } else {                          // tiny matrices: whole blocks per CTA
-        t_lo = ((nblk * blockIdx.x) / gridDim.x) * c.nchunk;
-        t_hi = ((nblk * (blockIdx.x + 1)) / gridDim.x) * c.nchunk;
-    }
-    c.rb_lo = (int)(t_lo / c.nchunk);
-    c.head_off = (int)(t_lo % c.nchunk);
-    if (t_hi > t_lo) {
-        c.nb = (int)((t_hi - 1) / c.nchunk) - c.rb_lo + 1;
-        c.tail_end = (int)((t_hi - 1) % c.nchunk) + 1;
-    } else {
-        c.nb = 0;
-        c.tail_end = c.nchunk;
-    }
     return c;
 }
 
@@ -226,33 +205,15 @@ __device__ __forceinline__ float mk_row_value(const float* s_gpart, int rb, int 
     return v;
 }
 
-// after the streaming loop: reduce the 16 K-slices, hand over / pick up blocks shared with the neighbour CTAs,
-// apply the epilogue, coalesced global writes
+// after the streaming loop: reduce the 16 K-slices, apply the epilogue, coalesced global writes
 template <int NB>
 __device__ __forceinline__ void mk_epilogue(const MegaParams& p, const MegaLayer* layers, int ph, const GemvCtx& c,
-                                            int B, int tid, int lane, int warp, const float* s_gpart, float res_pref,
-                                            bool have_res_pref, unsigned int seq) {
+                                            int B, int tid, const float* s_gpart, float res_pref, bool have_res_pref) {
     const PhaseIO io = mk_phase_io(p, layers, ph);
-    const bool head_shared = c.nb > 0 && c.head_off != 0;        // first block began in CTA blockIdx.x - 1
-    const bool tail_shared = c.nb > 0 && c.tail_end != c.nchunk;  // last block continues in CTA blockIdx.x + 1
-    // A: publish the partial sums of the block that continues in the next CTA
-    if (tail_shared && warp == 0) {
-        if (lane < 8 * NB) {
-            const int b = lane >> 3, r = lane & 7;
-            p.xcta_scratch[((size_t)blockIdx.x * NB + b) * 8 + r] = mk_row_value<NB>(s_gpart, c.nb - 1, b, r);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.xcta_flag + blockIdx.x), "r"(seq) : "memory");
-        }
-    }
-    // B: blocks streamed entirely by this CTA
-    const int lb_lo = head_shared ? 1 : 0, lb_hi = c.nb - (tail_shared ? 1 : 0);
     if (c.act == ACT_SWIGLU) {
-        const int nch = max(lb_hi - lb_lo, 0) * 4;
+        const int nch = c.nb * 4;
         for (int idx = tid; idx < nch * B; idx += MK_CONS) {
-            const int b = idx / nch, r = lb_lo * 4 + (idx - b * nch);  // local channel
+            const int b = idx / nch, r = idx - b * nch;
             const int rb = r >> 2, q = r & 3;
             const float gt = mk_row_value<NB>(s_gpart, rb, b, q);
             const float up = mk_row_value<NB>(s_gpart, rb, b, q + 4);
@@ -260,40 +221,12 @@ __device__ __forceinline__ void mk_epilogue(const MegaParams& p, const MegaLayer
                 __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
         }
     } else {
-        const int nr = max(lb_hi - lb_lo, 0) * 8;
+        const int nr = c.nb * 8;
         for (int idx = tid; idx < nr * B; idx += MK_CONS) {
-            const int b = idx / nr, r = lb_lo * 8 + (idx - b * nr);  // local row
+            const int b = idx / nr, r = idx - b * nr;
             float y = mk_row_value<NB>(s_gpart, r >> 3, b, r & 7);
             const size_t o = (size_t)b * io.ld_out + (size_t)c.rb_lo * 8 + r;
             if (io.residual != nullptr) y += have_res_pref ? res_pref : __bfloat162float(__ldcg(io.residual + o));
-            if (io.out_fp32) reinterpret_cast<float*>(io.out)[o] = y;
-            else reinterpret_cast<__nv_bfloat16*>(io.out)[o] = __float2bfloat16_rn(y);
-        }
-    }
-    // C: finish the block whose first tiles were streamed by the previous CTA (value = its partial + ours)
-    if (head_shared && warp == 1) {
-        if (lane == 0) {
-            unsigned int cur, spins = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(p.xcta_flag + blockIdx.x - 1) : "memory");
-                if (++spins > (1u << 26)) asm volatile("trap;");
-            } while (cur != seq);
-        }
-        __syncwarp();
-        const float* prev = p.xcta_scratch + (size_t)(blockIdx.x - 1) * NB * 8;
-        if (c.act == ACT_SWIGLU) {
-            if (lane < 4 * B) {
-                const int b = lane >> 2, q = lane & 3;
-                const float gt = __ldcg(prev + b * 8 + q) + mk_row_value<NB>(s_gpart, 0, b, q);
-                const float up = __ldcg(prev + b * 8 + q + 4) + mk_row_value<NB>(s_gpart, 0, b, q + 4);
-                reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + (size_t)c.rb_lo * 4 + q] =
-                    __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
-            }
-        } else if (lane < 8 * B) {
-            const int b = lane >> 3, r = lane & 7;
-            float y = __ldcg(prev + b * 8 + r) + mk_row_value<NB>(s_gpart, 0, b, r);
-            const size_t o = (size_t)b * io.ld_out + (size_t)c.rb_lo * 8 + r;
-            if (io.residual != nullptr) y += __bfloat162float(__ldcg(io.residual + o));
             if (io.out_fp32) reinterpret_cast<float*>(io.out)[o] = y;
             else reinterpret_cast<__nv_bfloat16*>(io.out)[o] = __float2bfloat16_rn(y);
         }
@@ -479,7 +412,7 @@ __device__ __forceinline__ void cursor_seek(TileCursor& t, const MegaParams& p, 
     while (t.ph < n_phases) {
         if (!mk_is_attention(p, t.ph)) {
             t.c = mk_phase_ctx(p, layers, t.ph);
-            if (t.c.nb > 0) { t.rb = 0; t.kc = t.c.head_off; t.valid = true; return; }
+            if (t.c.nb > 0) { t.rb = 0; t.kc = 0; t.valid = true; return; }
         }
         ++t.ph;
     }
@@ -491,7 +424,7 @@ __device__ __forceinline__ void cursor_begin(TileCursor& t, const MegaParams& p,
 }
 __device__ __forceinline__ void cursor_next(TileCursor& t, const MegaParams& p, const MegaLayer* layers, int n_phases) {
     ++t.tile;
-    if (++t.kc < (t.rb == t.c.nb - 1 ? t.c.tail_end : t.c.nchunk)) return;
+    if (++t.kc < t.c.nchunk) return;
     t.kc = 0;
     if (++t.rb < t.c.nb) return;
     ++t.ph;
@@ -615,12 +548,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             const PhaseIO io = mk_phase_io(p, s_layers, ph);
             // residual of the (<= 512) outputs this CTA writes: fetched now, consumed after the weight stream
             // (measured: takes ~1.5 us (o_proj) / 0.6 us (down) of L2 latency off the epilogue's critical path)
-            const int lb_lo = (c.nb > 0 && c.head_off != 0) ? 1 : 0;
-            const int nr_own = max(c.nb - ((c.nb > 0 && c.tail_end != c.nchunk) ? 1 : 0) - lb_lo, 0) * 8;
-            const bool have_res = io.residual != nullptr && nr_own * B <= MK_CONS;
+            const bool have_res = io.residual != nullptr && c.nb * 8 * B <= MK_CONS;
             float res_pref = 0.f;
-            if (have_res && tid < nr_own * B) {
-                const int b = tid / nr_own, r = lb_lo * 8 + (tid - b * nr_own);
+            if (have_res && tid < c.nb * 8 * B) {
+                const int nr = c.nb * 8, b = tid / nr, r = tid - b * nr;
                 res_pref = __bfloat162float(__ldcg(io.residual + (size_t)b * io.ld_out + (size_t)c.rb_lo * 8 + r));
             }
             mk_prologue<NB>(io, c.K, B, p.eps, tid, lane, warp, xs, s_red, s_rstd);
@@ -628,9 +559,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 #pragma unroll 1
             for (int rb = 0; rb < c.nb; ++rb) {
                 float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};  // two independent MMA chains
-                const int kc_lo = rb == 0 ? c.head_off : 0, kc_hi = rb == c.nb - 1 ? c.tail_end : c.nchunk;
 #pragma unroll 1
-                for (int kc = kc_lo; kc < kc_hi; ++kc, ++tile) {
+                for (int kc = 0; kc < c.nchunk; ++kc, ++tile) {
                     const uint32_t stage = tile % (uint32_t)n_stages;
                     const uint32_t parity = (tile / (uint32_t)n_stages) & 1u;
                     const int nk32 = min(MK_KT, c.K - kc * MK_KT) >> 5;
@@ -655,7 +585,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             }
             cons_sync();
             if (tracing) p.trace[ph * 4 + 2] = clock64();
-            mk_epilogue<NB>(p, s_layers, ph, c, B, tid, lane, warp, s_gpart, res_pref, have_res, bar_target);
+            mk_epilogue<NB>(p, s_layers, ph, c, B, tid, s_gpart, res_pref, have_res);
         }
         if (tracing) p.trace[ph * 4 + 3] = clock64();
         bar_target += gridDim.x;

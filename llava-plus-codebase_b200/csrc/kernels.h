@@ -106,8 +106,6 @@ struct MegaParams {
     float* attn_partial = nullptr;      // [B*H*nsplit*(128+2)]
     int32_t* attn_counters = nullptr;   // [B*H], zero-initialised, self-resetting
     unsigned int *bar_count = nullptr, *done_count = nullptr;  // zero-initialised
-    float* xcta_scratch = nullptr;       // [grid][NB][8] partial sums of blocks shared by neighbouring CTAs
-    unsigned int* xcta_flag = nullptr;   // [grid] zero-initialised
     unsigned int bar_base = 0;  // barrier-counter value before this launch = launches so far * (5L+2) * grid
     float eps = 1e-5f, theta = 10000.f, scale_log2 = 1.f;
     long long* trace = nullptr;  // optional [n_phases+2][4] SM-clock timestamps of CTA 0 (B2_MEGA_TRACE=1)

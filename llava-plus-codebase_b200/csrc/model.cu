@@ -442,8 +442,6 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     p.attn_partial = kv->attn_partial.as<float>(); p.attn_counters = kv->attn_counters.as<int32_t>();
     unsigned int* sync = kv->mega_sync.as<unsigned int>();
     p.bar_count = sync; p.done_count = sync + 2;
-    p.xcta_flag = sync + 16;                                  // [grid] uints
-    p.xcta_scratch = reinterpret_cast<float*>(sync + 16 + 512);  // [grid][NB<=2][8] floats
     p.bar_base = kv->mega_bar_base;
     kv->mega_bar_base += (unsigned int)(5 * d.layers + 2) * (unsigned int)num_sms();
     p.eps = d.rms_eps; p.theta = d.rope_theta;
@@ -737,12 +735,12 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
             tbl[l].kcache = kv->k.as<bf16>() + (size_t)l * kv->layer_stride();
             tbl[l].vcache = kv->v.as<bf16>() + (size_t)l * kv->layer_stride();
         }
-        if ((r = kv->mega_layers.alloc(tbl.size() * sizeof(MegaLayer))) != 0 || (r = kv->mega_sync.alloc(64 * 1024)) != 0) {
+        if ((r = kv->mega_layers.alloc(tbl.size() * sizeof(MegaLayer))) != 0 || (r = kv->mega_sync.alloc(64)) != 0) {
             b2_kv_destroy(kv);
             return r;
         }
         cudaMemcpy(kv->mega_layers.p, tbl.data(), tbl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice);
-        cudaMemset(kv->mega_sync.p, 0, 64 * 1024);
+        cudaMemset(kv->mega_sync.p, 0, 64);
     }
     if ((r = kv->out_tokens.alloc((size_t)kv->out_capacity * max_batch * 4)) != 0 ||
         (r = kv->attn_partial.alloc(((size_t)max_batch * m->d.heads * max_split + 1024) * (128 + 2) * 4)) != 0 ||
