@@ -231,8 +231,9 @@ def run_reference(args):
     S = P_IMG + args.prompt
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_sample(m, S, args.new, sample_layers=2 if i < args.warmup else 4,
-                                    decode_steps=2 if i < args.warmup else 4)
+        # warm-up steps use a smaller sample (thread pools, allocator); timed steps the bounded sample
+        last = cpu_reference_sample(m, S, args.new, sample_layers=1 if i < args.warmup else 2,
+                                    decode_steps=1 if i < args.warmup else 3)
         if i >= args.warmup:
             vals.append(last)
     value = sum(v["value"] for v in vals) / len(vals)
