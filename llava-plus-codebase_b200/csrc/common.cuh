@@ -141,6 +141,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("trap;");
 }
 
+// single non-blocking probe (1 = phase with this parity has completed)
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done;
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — 2D tiled load, completion on an mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -41,8 +41,8 @@ constexpr int MK_TILE_BYTES = 8 * MK_ROW_STRIDE;
 constexpr int MK_MAXNB = 32;                  // max 8-row blocks per CTA per phase (host-checked)
 constexpr int MK_MAXL = 48;                   // decoder layers whose weight-pointer table is cached in smem
 constexpr int MK_MAX_STAGES = 12;
-constexpr int MK_L2_AHEAD = 0;                // tiles prefetched into L2 beyond the ring (multiple of MK_PROD_WARPS). Measured: 16
-                                              // tiles (38 MB chip-wide) made the step 5% SLOWER (extra TMA issue work, no gain) -> off
+constexpr int MK_L2_AHEAD = 8;                // tiles (32 KB each, x148 CTAs = 38 MB) prefetched into L2 beyond the ring, only while
+                                              // the producer is stalled on a full ring
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
@@ -473,28 +473,42 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 
     if (warp >= MK_CONS_WARPS) {
         // =========================== PRODUCERS: stream every phase's weight tiles, in order ===========================
-        // Two cursors walk the same tile sequence: `cp` feeds the shared-memory ring with TMA bulk copies (throttled
-        // by free ring slots), `pf` runs MK_L2_AHEAD tiles ahead of it issuing bulk L2 prefetches (no smem needed), so
-        // while the consumers sit in a barrier/prologue and the ring is full, HBM keeps streaming the next phase's
-        // weights into the 126 MB L2 and the ring refills from L2 afterwards.
+        // `cp` feeds the shared-memory ring with TMA bulk copies, throttled by free ring slots. While a producer
+        // warp is stalled on a full ring (the consumers sit in a barrier / prologue / attention), it spends the idle
+        // time issuing bulk L2 prefetches for its own tiles just BEYOND the ring (`pf`, at most MK_L2_AHEAD tiles
+        // further), so HBM keeps streaming into the 126 MB L2 during the dependency and the ring refills from L2
+        // afterwards. (Prefetching unconditionally for every tile doubled the TMA issue work and was 5% slower.)
         const uint32_t pw = (uint32_t)(warp - MK_CONS_WARPS);
         TileCursor cp, pf;
         cursor_begin(cp, p, s_layers, n_phases);
         cursor_begin(pf, p, s_layers, n_phases);
-        for (int i = 0; i < MK_L2_AHEAD && pf.valid; ++i) {
-            if (pf.tile % (uint32_t)MK_PROD_WARPS == pw && lane < 8) {
-                const uint32_t row_bytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
-                bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
-                                     (size_t)pf.kc * MK_KT, row_bytes);
-            }
-            cursor_next(pf, p, s_layers, n_phases);
-        }
         while (cp.valid) {
             if (cp.tile % (uint32_t)MK_PROD_WARPS == pw) {
                 const uint32_t stage = cp.tile % (uint32_t)n_stages;
                 const uint32_t parity = (cp.tile / (uint32_t)n_stages) & 1u;
                 const uint32_t row_bytes = (uint32_t)min(MK_KT, cp.c.K - cp.kc * MK_KT) * 2u;
-                if (lane == 0) {
+                if (MK_L2_AHEAD > 0) {
+                    // keep pf on this warp's first tile beyond the ring
+                    while (pf.valid && (pf.tile < cp.tile + (uint32_t)n_stages || pf.tile % (uint32_t)MK_PROD_WARPS != pw))
+                        cursor_next(pf, p, s_layers, n_phases);
+                    uint32_t spins = 0;
+                    for (;;) {
+                        uint32_t ready = 0;
+                        if (lane == 0) ready = mbar_try_wait(&empty_bar[stage], parity ^ 1u);
+                        ready = __shfl_sync(0xffffffffu, ready, 0);
+                        if (ready) break;
+                        if (pf.valid && pf.tile < cp.tile + (uint32_t)n_stages + (uint32_t)MK_L2_AHEAD) {
+                            if (lane < 8) {
+                                const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
+                                bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
+                                                     (size_t)pf.kc * MK_KT, pbytes);
+                            }
+                            for (int i = 0; i < MK_PROD_WARPS && pf.valid; ++i) cursor_next(pf, p, s_layers, n_phases);
+                        }
+                        if (++spins > (1u << 24)) asm volatile("trap;");
+                    }
+                    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], 8u * row_bytes);
+                } else if (lane == 0) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);  // slot drained by all consumer warps
                     mbar_arrive_expect_tx(&full_bar[stage], 8u * row_bytes);
                 }
@@ -503,14 +517,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                     bulk_g2s(ring + (size_t)stage * MK_TILE_BYTES + (size_t)lane * MK_ROW_STRIDE,
                              cp.c.W + (size_t)mk_phys_row(cp.c.act, cp.c.rb_lo + cp.rb, lane) * cp.c.K +
                                  (size_t)cp.kc * MK_KT, row_bytes, &full_bar[stage]);
-                if (MK_L2_AHEAD > 0 && pf.valid && lane < 8) {  // pf.tile == cp.tile + MK_L2_AHEAD: same residue mod MK_PROD_WARPS
-                    const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
-                    bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
-                                         (size_t)pf.kc * MK_KT, pbytes);
-                }
             }
             cursor_next(cp, p, s_layers, n_phases);
-            if (MK_L2_AHEAD > 0 && pf.valid) cursor_next(pf, p, s_layers, n_phases);
         }
         return;
     }
