@@ -41,8 +41,8 @@ constexpr int MK_TILE_BYTES = 8 * MK_ROW_STRIDE;
 constexpr int MK_MAXNB = 32;                  // max 8-row blocks per CTA per phase (host-checked)
 constexpr int MK_MAXL = 48;                   // decoder layers whose weight-pointer table is cached in smem
 constexpr int MK_MAX_STAGES = 12;
-constexpr int MK_L2_AHEAD = 8;                // tiles (32 KB each, x148 CTAs = 38 MB) prefetched into L2 beyond the ring, only while
-                                              // the producer is stalled on a full ring
+constexpr int MK_L2_AHEAD = 0;                // optional L2 bulk prefetch beyond the ring while the producer is stalled. MEASURED
+                                              // HARMFUL on B200 (8 tiles: 4.18 vs 2.81 ms/token; unconditional 16 tiles: 3.24) -> off
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
