@@ -77,13 +77,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
-// one GEMV phase as seen by a CTA: rows are grouped into logical 8-row blocks (SwiGLU: 4 gate rows + the 4 up
-// rows of the same channels); CTA c owns the contiguous block range [rb_lo, rb_lo + nb)
+// One GEMV phase as seen by a CTA. Output units (rows; SwiGLU: channels = a gate row + its up row) are cut into
+// gridDim.x contiguous ranges that differ by at most ONE unit, so every SM streams the same number of bytes to
+// within 1-4% (a split in whole 8-row blocks left +-1 block = 6-16% skew per phase in front of every grid barrier:
+// profiles/r1c_mega_phase_trace_v4.txt). The range is walked in MMA-sized blocks of 8 rows (SwiGLU: 4 gate rows +
+// the 4 up rows of the same channels); the last block may be partial — its missing rows are simply not fetched.
 struct GemvCtx {
     const __nv_bfloat16* W;
     int K, act;
-    int rb_lo, nb;
-    int nchunk;  // K tiles per block
+    int u_lo, nu;   // first output unit (row / channel) and number of units owned by this CTA
+    int nb;         // blocks: ceil(nu / 8) (SwiGLU: ceil(nu / 4))
+    int nchunk;     // K tiles per block
 };
 // cold per-phase I/O, recomputed from the phase index where needed (prologue, epilogue)
 struct PhaseIO {
@@ -94,13 +98,23 @@ struct PhaseIO {
     int ld_out, out_fp32;
 };
 
-// physical weight row of lane-group g (0..7) of logical block `blk`
-__device__ __forceinline__ int mk_phys_row(int act, int blk, int g) {
-    if (act == ACT_SWIGLU) {  // block-64 interleaved gate/up: g<4 -> gate of channel 4*blk+g, g>=4 -> up of 4*blk+g-4
-        const int ch = blk * 4 + (g & 3);
+// physical weight row of lane-group g (0..7) of the CTA's local block `rb`; `valid` = the row exists in this CTA's range
+__device__ __forceinline__ int mk_phys_row(const GemvCtx& c, int rb, int g, bool& valid) {
+    if (c.act == ACT_SWIGLU) {  // block-64 interleaved gate/up: g<4 -> gate of local channel 4*rb+g, g>=4 -> its up row
+        const int lc = rb * 4 + (g & 3);
+        valid = lc < c.nu;
+        const int ch = c.u_lo + lc;
         return (ch >> 6) * 128 + (ch & 63) + ((g >> 2) ? 64 : 0);
     }
-    return blk * 8 + g;
+    const int lr = rb * 8 + g;
+    valid = lr < c.nu;
+    return c.u_lo + lr;
+}
+
+// rows actually fetched for local block rb (8, or fewer for the partial last block)
+__device__ __forceinline__ int mk_rows_in_block(const GemvCtx& c, int rb) {
+    if (c.act == ACT_SWIGLU) return 2 * min(4, c.nu - rb * 4);
+    return min(8, c.nu - rb * 8);
 }
 
 // phase k of layer l (k: 0 = QKV, 1 = attention, 2 = o_proj, 3 = gate/up, 4 = down); index 5L = lm_head
@@ -127,9 +141,10 @@ __device__ __forceinline__ GemvCtx mk_phase_ctx(const MegaParams& p, const MegaL
     else if (k == 2) { c.W = layers[l].wo; N = p.h; c.K = p.h; }
     else if (k == 3) { c.W = layers[l].wgu; N = 2 * p.I; c.K = p.h; c.act = ACT_SWIGLU; }
     else { c.W = layers[l].wd; N = p.h; c.K = p.I; }
-    const long long nblk = N >> 3;
-    c.rb_lo = (int)((nblk * blockIdx.x) / gridDim.x);
-    c.nb = (int)((nblk * (blockIdx.x + 1)) / gridDim.x) - c.rb_lo;
+    const long long units = c.act == ACT_SWIGLU ? (N >> 1) : N;
+    c.u_lo = (int)((units * blockIdx.x) / gridDim.x);
+    c.nu = (int)((units * (blockIdx.x + 1)) / gridDim.x) - c.u_lo;
+    c.nb = c.act == ACT_SWIGLU ? (c.nu + 3) >> 2 : (c.nu + 7) >> 3;
     c.nchunk = (c.K + MK_KT - 1) / MK_KT;
     return c;
 }
@@ -211,21 +226,21 @@ __device__ __forceinline__ void mk_epilogue(const MegaParams& p, const MegaLayer
                                             int B, int tid, const float* s_gpart, float res_pref, bool have_res_pref) {
     const PhaseIO io = mk_phase_io(p, layers, ph);
     if (c.act == ACT_SWIGLU) {
-        const int nch = c.nb * 4;
+        const int nch = c.nu;
         for (int idx = tid; idx < nch * B; idx += MK_CONS) {
             const int b = idx / nch, r = idx - b * nch;
             const int rb = r >> 2, q = r & 3;
             const float gt = mk_row_value<NB>(s_gpart, rb, b, q);
             const float up = mk_row_value<NB>(s_gpart, rb, b, q + 4);
-            reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + (size_t)c.rb_lo * 4 + r] =
+            reinterpret_cast<__nv_bfloat16*>(io.out)[(size_t)b * io.ld_out + (size_t)c.u_lo + r] =
                 __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
         }
     } else {
-        const int nr = c.nb * 8;
+        const int nr = c.nu;
         for (int idx = tid; idx < nr * B; idx += MK_CONS) {
             const int b = idx / nr, r = idx - b * nr;
             float y = mk_row_value<NB>(s_gpart, r >> 3, b, r & 7);
-            const size_t o = (size_t)b * io.ld_out + (size_t)c.rb_lo * 8 + r;
+            const size_t o = (size_t)b * io.ld_out + (size_t)c.u_lo + r;
             if (io.residual != nullptr) y += have_res_pref ? res_pref : __bfloat162float(__ldcg(io.residual + o));
             if (io.out_fp32) reinterpret_cast<float*>(io.out)[o] = y;
             else reinterpret_cast<__nv_bfloat16*>(io.out)[o] = __float2bfloat16_rn(y);
@@ -498,25 +513,27 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                         ready = __shfl_sync(0xffffffffu, ready, 0);
                         if (ready) break;
                         if (pf.valid && pf.tile < cp.tile + (uint32_t)n_stages + (uint32_t)MK_L2_AHEAD) {
-                            if (lane < 8) {
+                            bool pvalid;
+                            const int pfrow = mk_phys_row(pf.c, pf.rb, lane & 7, pvalid);
+                            if (lane < 8 && pvalid) {
                                 const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
-                                bulk_prefetch_l2(pf.c.W + (size_t)mk_phys_row(pf.c.act, pf.c.rb_lo + pf.rb, lane) * pf.c.K +
-                                                     (size_t)pf.kc * MK_KT, pbytes);
+                                bulk_prefetch_l2(pf.c.W + (size_t)pfrow * pf.c.K + (size_t)pf.kc * MK_KT, pbytes);
                             }
                             for (int i = 0; i < MK_PROD_WARPS && pf.valid; ++i) cursor_next(pf, p, s_layers, n_phases);
                         }
                         if (++spins > (1u << 24)) asm volatile("trap;");
                     }
-                    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], 8u * row_bytes);
+                    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)mk_rows_in_block(cp.c, cp.rb) * row_bytes);
                 } else if (lane == 0) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);  // slot drained by all consumer warps
-                    mbar_arrive_expect_tx(&full_bar[stage], 8u * row_bytes);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)mk_rows_in_block(cp.c, cp.rb) * row_bytes);
                 }
                 __syncwarp();
-                if (lane < 8)
+                bool row_valid;
+                const int prow = mk_phys_row(cp.c, cp.rb, lane & 7, row_valid);
+                if (lane < 8 && row_valid)
                     bulk_g2s(ring + (size_t)stage * MK_TILE_BYTES + (size_t)lane * MK_ROW_STRIDE,
-                             cp.c.W + (size_t)mk_phys_row(cp.c.act, cp.c.rb_lo + cp.rb, lane) * cp.c.K +
-                                 (size_t)cp.kc * MK_KT, row_bytes, &full_bar[stage]);
+                             cp.c.W + (size_t)prow * cp.c.K + (size_t)cp.kc * MK_KT, row_bytes, &full_bar[stage]);
             }
             cursor_next(cp, p, s_layers, n_phases);
         }
@@ -556,11 +573,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             const PhaseIO io = mk_phase_io(p, s_layers, ph);
             // residual of the (<= 512) outputs this CTA writes: fetched now, consumed after the weight stream
             // (measured: takes ~1.5 us (o_proj) / 0.6 us (down) of L2 latency off the epilogue's critical path)
-            const bool have_res = io.residual != nullptr && c.nb * 8 * B <= MK_CONS;
+            const bool have_res = io.residual != nullptr && c.nu * B <= MK_CONS;
             float res_pref = 0.f;
-            if (have_res && tid < c.nb * 8 * B) {
-                const int nr = c.nb * 8, b = tid / nr, r = tid - b * nr;
-                res_pref = __bfloat162float(__ldcg(io.residual + (size_t)b * io.ld_out + (size_t)c.rb_lo * 8 + r));
+            if (have_res && tid < c.nu * B) {
+                const int b = tid / c.nu, r = tid - b * c.nu;
+                res_pref = __bfloat162float(__ldcg(io.residual + (size_t)b * io.ld_out + (size_t)c.u_lo + r));
             }
             mk_prologue<NB>(io, c.K, B, p.eps, tid, lane, warp, xs, s_red, s_rstd);
             if (tracing) p.trace[ph * 4 + 1] = clock64();
