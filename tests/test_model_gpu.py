@@ -280,6 +280,34 @@ def test_7b_layer_shapes_prefill_decode_consistency():
     eng.close()
 
 
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_13b_layer_shapes_decode_equals_prefill_recompute(B):
+    """LLaVA-1.5-13B layer shapes (h=5120, I=13824, 40 heads; 2 layers): size-independent property at BASELINE
+    config-4 dims — the logits of a decode step (B<=2: persistent megakernel with its 5-stage TMA ring; B=4: GEMV
+    kernels from a CUDA graph) must equal the logits of a prefill over the extended sequence (tcgen05 GEMM + flash)."""
+    cfg = O.make_config(hidden=5120, inter=13824, layers=2, heads=40, vit_layers=2)
+    w = O.make_weights(cfg, seed=7)
+    eng = make_engine(cfg, w, max_batch=4, max_seq=256, max_images=1)
+    g = torch.Generator().manual_seed(3)
+    S_ = 150
+    embeds = (torch.randn(B, S_, cfg["hidden"], generator=g) * 0.5).to(torch.bfloat16)
+    kv = eng.new_kv(B, 256)
+    last = eng.prefill(kv, embeds.to(DEV), None, _b2.LOGITS_LAST)
+    toks = last.argmax(-1).to(torch.int32)
+    ext = embeds
+    for step in range(3):
+        lg = eng.decode_step(kv, toks)
+        ext = torch.cat([ext, w["model.embed_tokens.weight"][toks.cpu().long()][:, None].to(torch.bfloat16)], 1)
+        kv2 = eng.new_kv(B, 256)
+        ref = eng.prefill(kv2, ext.to(DEV), None, _b2.LOGITS_LAST)
+        _check(f"13B-shape decode step {step} vs prefill recompute (B={B})", lg, ref, tol_max=0.03, tol_mean=0.006)
+        kv2.close()
+        toks = lg.argmax(-1).to(torch.int32)
+    assert kv.lengths(B) == [S_ + 3] * B
+    kv.close()
+    eng.close()
+
+
 def test_decode_batch_above_8_uses_gemm_path_and_matches_oracle():
     """B > 8 decode runs the skinny-M tcgen05 GEMM path (+ CUDA-graph replay); B <= 8 the persistent megakernel.
     Both must agree with the oracle and with each other on the shared samples."""
