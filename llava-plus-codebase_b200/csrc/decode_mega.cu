@@ -203,55 +203,6 @@ __device__ __forceinline__ void mk_prologue(const PhaseIO& c, int K, int B, floa
     cons_sync();
 }
 
-// o_proj prologue when the attention output is still split over G (2..4) per-CTA partials: x[b][8i..8i+8) =
-// sum_s w_s * o_s / sum_s w_s * l_s with w_s = 2^(m_s - max m). All 5*G 8-byte loads of a thread are independent
-// and issued before the first use (one L2 round trip), the merge order is fixed (deterministic).
-template <int NB>
-__device__ __forceinline__ void mk_prologue_attn(const float* attn_partial, int G, int H, int K, int B, int tid,
-                                                 __nv_bfloat16* xs) {
-    const int nvec = K >> 3;
-    for (int i = tid; i < nvec; i += MK_CONS) {
-        const int head = (i * 8) / MK_D, d0 = (i * 8) % MK_D;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            uint4 outv = make_uint4(0, 0, 0, 0);
-            if (b < B) {
-                const float* pb = attn_partial + (size_t)(b * H + head) * G * (MK_D + 2);
-                float2 ml[4], o[4][4];
-#pragma unroll
-                for (int sidx = 0; sidx < 4; ++sidx) {
-                    const float* ps = pb + (size_t)min(sidx, G - 1) * (MK_D + 2);
-                    ml[sidx] = __ldcg(reinterpret_cast<const float2*>(ps + MK_D));
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) o[sidx][q] = __ldcg(reinterpret_cast<const float2*>(ps + d0 + 2 * q));
-                }
-                float m_all = -INFINITY;
-#pragma unroll
-                for (int sidx = 0; sidx < 4; ++sidx)
-                    if (sidx < G) m_all = fmaxf(m_all, ml[sidx].x);
-                float l_all = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int sidx = 0; sidx < 4; ++sidx) {
-                    if (sidx < G) {
-                        const float wgt = (ml[sidx].x == -INFINITY) ? 0.f : exp2f(ml[sidx].x - m_all);
-                        l_all += ml[sidx].y * wgt;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            acc[2 * q] += o[sidx][q].x * wgt;
-                            acc[2 * q + 1] += o[sidx][q].y * wgt;
-                        }
-                    }
-                }
-                const float inv = 1.f / l_all;
-                outv = make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv),
-                                  pack_bf16(acc[4] * inv, acc[5] * inv), pack_bf16(acc[6] * inv, acc[7] * inv));
-            }
-            *reinterpret_cast<uint4*>(xs + (size_t)b * K + i * 8) = outv;
-        }
-    }
-    cons_sync();
-}
-
 __device__ __forceinline__ void mk_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
     // A rows 8..15 (a1, a3) are the zero padding of the batch dimension
     asm volatile(
@@ -308,7 +259,7 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
     const int h = p.h, H = p.H;
     const int pairs = p.B * H;
     const int grid = gridDim.x;
-    const int G = pairs <= grid ? min(grid / pairs, 4) : 1;
+    const int G = pairs <= grid ? grid / pairs : 1;
     const int hw = lane >> 4, c = lane & 15;
     const int split = pairs <= grid ? (int)blockIdx.x % G : 0;
     for (int pair = pairs <= grid ? (int)blockIdx.x / G : (int)blockIdx.x; pair < pairs;
@@ -432,13 +383,33 @@ __device__ __forceinline__ void mk_attention(const MegaParams& p, const MegaLaye
         }
         if (G == 1) {
             if (tid < MK_D) p.attn[(size_t)b * h + head * MK_D + tid] = __float2bfloat16_rn(o_cta / l_cta);
-        } else if (tid < MK_D) {
-            // per-CTA partial (o, m, l). The grid barrier that follows publishes it; every CTA's o_proj prologue then
-            // merges the G partials while staging its activations (mk_prologue_attn) — no fence + atomic + last-CTA
-            // merge chain (~2.5 us) at the end of the attention phase.
+        } else {
             float* part = p.attn_partial + ((size_t)pair * G + split) * (MK_D + 2);
-            part[tid] = o_cta;
-            if (tid == 0) { part[MK_D] = m_cta; part[MK_D + 1] = l_cta; }
+            if (tid < MK_D) {
+                part[tid] = o_cta;
+                if (tid == 0) { part[MK_D] = m_cta; part[MK_D + 1] = l_cta; }
+            }
+            __threadfence();
+            cons_sync();
+            if (tid == 0) *s_flag = (atomicAdd(&p.attn_counters[pair], 1) == G - 1) ? 1 : 0;
+            cons_sync();
+            if (*s_flag) {  // last CTA of this (b, head): merge the G partials
+                __threadfence();
+                if (tid < MK_D) {
+                    const float* pb = p.attn_partial + (size_t)pair * G * (MK_D + 2);
+                    float m_all = -INFINITY;
+                    for (int sidx = 0; sidx < G; ++sidx) m_all = fmaxf(m_all, __ldcg(pb + (size_t)sidx * (MK_D + 2) + MK_D));
+                    float l_all = 0.f, o_all = 0.f;
+                    for (int sidx = 0; sidx < G; ++sidx) {
+                        const float ms = __ldcg(pb + (size_t)sidx * (MK_D + 2) + MK_D);
+                        const float wgt = (ms == -INFINITY) ? 0.f : exp2f(ms - m_all);
+                        l_all += __ldcg(pb + (size_t)sidx * (MK_D + 2) + MK_D + 1) * wgt;
+                        o_all += __ldcg(pb + (size_t)sidx * (MK_D + 2) + tid) * wgt;
+                    }
+                    p.attn[(size_t)b * h + head * MK_D + tid] = __float2bfloat16_rn(o_all / l_all);
+                    if (tid == 0) p.attn_counters[pair] = 0;
+                }
+            }
         }
         cons_sync();  // s_part / s_flag are reused by the next pair
     }
@@ -591,7 +562,6 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
     const int g = lane >> 2, t4 = lane & 3;
-    const int attn_G = (B * p.H <= (int)gridDim.x) ? min((int)gridDim.x / (B * p.H), 4) : 1;  // CTAs sharing one (b, head)
     uint32_t tile = 0;
 #pragma unroll 1
     for (int ph = 0; ph < n_phases; ++ph) {
@@ -609,10 +579,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                 const int b = tid / c.nu, r = tid - b * c.nu;
                 res_pref = __bfloat162float(__ldcg(io.residual + (size_t)b * io.ld_out + (size_t)c.u_lo + r));
             }
-            if (ph % 5 == 2 && ph < 5 * p.L && attn_G > 1)
-                mk_prologue_attn<NB>(p.attn_partial, attn_G, p.H, c.K, B, tid, xs);
-            else
-                mk_prologue<NB>(io, c.K, B, p.eps, tid, lane, warp, xs, s_red, s_rstd);
+            mk_prologue<NB>(io, c.K, B, p.eps, tid, lane, warp, xs, s_red, s_rstd);
             if (tracing) p.trace[ph * 4 + 1] = clock64();
 #pragma unroll 1
             for (int rb = 0; rb < c.nb; ++rb) {

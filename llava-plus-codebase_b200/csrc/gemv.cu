@@ -1,11 +1,19 @@
-// Weight-streaming GEMV for the one-token decode step (batch <= 8):
+// Weight-streaming GEMV for the one-token decode step outside the megakernel (batch 3..8, prefill's last-position
+// lm_head, B2_DECODE_MEGA=0):
 //     out[B, N] = (RMSNorm(x) | x)[B, K] · W[N, K]^T  (+ residual)      or the fused SwiGLU variant.
-// This is the HBM-bound hot loop of LLaVA decode: every weight byte is read
-// exactly once per step with 16-byte coalesced, L1-bypassing loads; a persistent grid of one 512-thread CTA
-// per SM keeps >= 8 independent 16 B loads in flight per lane through a register double buffer, and the
-// first weight loads are issued BEFORE the activation prologue (x -> smem, fused RMSNorm), since weights do
-// not depend on the previous kernel's output. Tensor cores are deliberately not used: at B <= 8 the op is
-// >20x below the tensor roofline and purely bandwidth-limited.
+// HBM-bound: every weight byte is read exactly once with 16-byte coalesced,
+// L1-bypassing loads from a persistent grid (one 512-thread CTA per SM, 16 loads in flight per lane through a
+// register double buffer; the first loads are issued BEFORE the activation prologue since weights do not depend
+// on the previous kernel's output).
+// The arithmetic runs on the tensor cores: mma.sync.m16n8k16 (bf16 x bf16 -> fp32) with the activations as the
+// A operand (rows = batch, zero padded to 16) and 8 weight rows as the B operand. One 16-byte load per lane
+// (weight row g = lane/4, 8 consecutive k at (lane%4)*8) feeds TWO MMAs with no unpacking, because the k index
+// is permuted identically on both operands (a dot product does not care). ~5 instructions per 16 B of weights for
+// any batch <= 8, against ~40 (B=1) .. ~250 (B=8) for the scalar bf16->fp32 FMA loop this replaces, which ncu
+// showed to be issue-bound (profiles/r1a_prof_gemv_ncu_full.txt).
+// CTA c owns a contiguous range of output rows (SwiGLU: channels) that differs by at most one unit between CTAs,
+// walked in 8-row blocks (last one partial: missing rows are not fetched); its 16 warps split K, the 16 partial
+// sums per output are reduced through shared memory in a fixed order (deterministic).
 // Reference math replaced: transformers modeling_llama.py:62-67 (RMSNorm), :182-184 (LlamaMLP),
 // :251-289 (q/k/v/o projections), llava_llama.py:48 (lm_head).
 #include "common.cuh"
@@ -16,8 +24,7 @@ namespace {
 
 constexpr int GV_THREADS = 512;
 constexpr int GV_WARPS = GV_THREADS / 32;
-constexpr int GV_R = 2;  // weight rows per work item
-constexpr int GV_U = 4;  // 256-element K-chunks per pipeline step
+constexpr int GV_UB = 8;  // 16-byte loads per lane per pipeline batch
 
 struct GemvParams {
     const __nv_bfloat16* x; int64_t ldx;
@@ -26,6 +33,7 @@ struct GemvParams {
     const __nv_bfloat16* residual; int ld_res;
     void* out; int ld_out; int out_fp32;
     int B, N, K, act;
+    int nb_max;  // blocks per CTA bound used for the smem partial table
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -33,53 +41,83 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
 
+__device__ __forceinline__ void gv_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    // A rows 8..15 (a1, a3) are the zero padding of the batch dimension
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+struct Ctx {
+    int u_lo, nu, nb;    // output units (rows / SwiGLU channels) of this CTA, blocks of 8 rows
+    int ks_lo, ks_len;   // this warp's K slice in 32-element blocks
+};
+
+// physical weight row of lane-group g of local block rb; valid = the row belongs to this CTA's range
+__device__ __forceinline__ int gv_phys_row(const GemvParams& p, const Ctx& c, int rb, int g, bool& valid) {
+    if (p.act == ACT_SWIGLU) {  // block-64 interleaved gate/up: g<4 -> gate of local channel 4*rb+g, g>=4 -> its up row
+        const int lc = rb * 4 + (g & 3);
+        valid = lc < c.nu;
+        const int ch = c.u_lo + lc;
+        return (ch >> 6) * 128 + (ch & 63) + ((g >> 2) ? 64 : 0);
+    }
+    const int lr = rb * 8 + g;
+    valid = lr < c.nu;
+    return c.u_lo + lr;
+}
+
+// issue the loads of batch bt (units 8*bt ..; unit u = (block u / ks_len, k32 ks_lo + u % ks_len)); buf fully defined
+__device__ __forceinline__ void gv_issue(const GemvParams& p, const Ctx& c, int bt, int lane, uint4 (&buf)[GV_UB]) {
+    const int u0 = bt * GV_UB;
+    const int U = c.nb * c.ks_len;
+    if (u0 < U) {
+        const int g = lane >> 2, t = lane & 3;
+        int rb = u0 / c.ks_len;
+        int kk = u0 - rb * c.ks_len;
+        bool valid;
+        int row = gv_phys_row(p, c, rb, g, valid);
+        const __nv_bfloat16* wr = p.W + (size_t)row * p.ldw + (size_t)c.ks_lo * 32 + t * 8;
+#pragma unroll
+        for (int j = 0; j < GV_UB; ++j) {
+            buf[j] = (u0 + j < U && valid) ? ld_stream_16(wr + kk * 32) : make_uint4(0, 0, 0, 0);
+            if (++kk == c.ks_len) {
+                kk = 0;
+                ++rb;
+                row = gv_phys_row(p, c, rb, g, valid);
+                wr = p.W + (size_t)row * p.ldw + (size_t)c.ks_lo * 32 + t * 8;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < GV_UB; ++j) buf[j] = make_uint4(0, 0, 0, 0);
+    }
+}
+
 template <int NB>
 __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(GemvParams p) {
     extern __shared__ __align__(16) uint8_t gv_smem[];
-    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gv_smem);  // [NB][K]
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gv_smem);                               // [NB][K]
+    float* s_part = reinterpret_cast<float*>(gv_smem + (size_t)NB * p.K * 2);                    // [16][nb_max][NB][8]
     __shared__ float s_red[GV_WARPS][NB];
     __shared__ float s_rstd[NB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gw = blockIdx.x * GV_WARPS + warp;
-    const int total_warps = gridDim.x * GV_WARPS;
     const int K = p.K;
-    const int nchunks = K >> 8;                       // K % 256 == 0
-    const int G = (nchunks + GV_U - 1) / GV_U;        // pipeline steps per item
-    const int n_items = p.N / GV_R;
-    const int n_my = gw < n_items ? (n_items - gw + total_warps - 1) / total_warps : 0;
-    const int total_steps = n_my * G;
-    const bool swiglu = p.act == ACT_SWIGLU;
+    Ctx c;
+    {
+        const long long units = p.act == ACT_SWIGLU ? (p.N >> 1) : p.N;
+        c.u_lo = (int)((units * blockIdx.x) / gridDim.x);
+        c.nu = (int)((units * (blockIdx.x + 1)) / gridDim.x) - c.u_lo;
+        c.nb = p.act == ACT_SWIGLU ? (c.nu + 3) >> 2 : (c.nu + 7) >> 3;
+        const int nk32 = K >> 5;
+        c.ks_lo = (nk32 * warp) / GV_WARPS;
+        c.ks_len = (nk32 * (warp + 1)) / GV_WARPS - c.ks_lo;
+    }
 
-    auto item_rows = [&](int item, int& r0, int& r1) {
-        if (swiglu) {  // item = output channel; gate/up rows are block-64 interleaved
-            r0 = (item >> 6) * 128 + (item & 63);
-            r1 = r0 + 64;
-        } else {
-            r0 = item * 2;
-            r1 = r0 + 1;
-        }
-    };
-    auto issue = [&](int s, uint4 (&buf)[GV_R][GV_U]) {
-        if (s < total_steps) {
-            const int item = gw + (s / G) * total_warps;
-            const int g = s % G;
-            int rr[2];
-            item_rows(item, rr[0], rr[1]);
-#pragma unroll
-            for (int r = 0; r < GV_R; ++r) {
-                const __nv_bfloat16* wr = p.W + (size_t)rr[r] * p.ldw + lane * 8;
-#pragma unroll
-                for (int u = 0; u < GV_U; ++u) {
-                    const int ch = g * GV_U + u;
-                    buf[r][u] = (ch < nchunks) ? ld_stream_16(wr + ch * 256) : make_uint4(0, 0, 0, 0);
-                }
-            }
-        }
-    };
-
-    uint4 bufA[GV_R][GV_U], bufB[GV_R][GV_U];
-    issue(0, bufA);  // weights do not depend on x: get HBM requests in flight before the prologue
+    uint4 bufA[GV_UB], bufB[GV_UB];
+    gv_issue(p, c, 0, lane, bufA);  // weights do not depend on x: get HBM requests in flight before the prologue
+    gv_issue(p, c, 1, lane, bufB);
 
     // ---------------- prologue: x -> smem (bf16), optional fused RMSNorm ----------------
     {
@@ -115,16 +153,14 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(GemvParams p) {
             }
             __syncthreads();
             for (int i = tid; i < nvec; i += GV_THREADS) {
-                const uint4 gq = *reinterpret_cast<const uint4*>(p.gamma + i * 8);
                 float gf[8];
-                unpack8(gq, gf);
+                unpack8(*reinterpret_cast<const uint4*>(p.gamma + i * 8), gf);
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     uint4* px = reinterpret_cast<uint4*>(xs + (size_t)b * K + i * 8);
-                    float f[8];
+                    float f[8], o[8];
                     unpack8(*px, f);
                     const float rstd = s_rstd[b];
-                    float o[8];
                     // HF LlamaRMSNorm: weight * (x * rstd).to(bf16), result in bf16
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = gf[e] * round_bf16(f[e] * rstd);
@@ -136,102 +172,111 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(GemvParams p) {
         __syncthreads();
     }
 
-    // ---------------- main loop ----------------
-    float acc[GV_R][NB];
-    auto compute = [&](int s, const uint4 (&buf)[GV_R][GV_U]) {
-        if (s >= total_steps) return;
-        const int item = gw + (s / G) * total_warps;
-        const int g = s % G;
-        if (g == 0) {
+    // ---------------- main loop: tensor-core dot products over this warp's K slice of every block ----------------
+    {
+        const int g = lane >> 2, t = lane & 3;
+        const int U = c.nb * c.ks_len;
+        const int n_batches = (U + GV_UB - 1) / GV_UB;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        int rb = 0, kk = 0;
+        auto compute = [&](int bt, const uint4 (&buf)[GV_UB]) {
+            const int u0 = bt * GV_UB;
+            if (u0 >= U) return;
 #pragma unroll
-            for (int r = 0; r < GV_R; ++r)
-#pragma unroll
-                for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < GV_U; ++u) {
-            const int ch = g * GV_U + u;
-            if (ch < nchunks) {
-                float w0[8], w1[8];
-                unpack8(buf[0][u], w0);
-                unpack8(buf[1][u], w1);
-                const int koff = ch * 256 + lane * 8;
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    float xf[8];
-                    unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)b * K + koff), xf);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        acc[0][b] = fmaf(w0[e], xf[e], acc[0][b]);
-                        acc[1][b] = fmaf(w1[e], xf[e], acc[1][b]);
+            for (int j = 0; j < GV_UB; ++j) {
+                if (u0 + j < U) {  // warp-uniform
+                    uint4 xv = make_uint4(0, 0, 0, 0);
+                    if (g < p.B) xv = *reinterpret_cast<const uint4*>(xs + (size_t)g * K + (size_t)(c.ks_lo + kk) * 32 + t * 8);
+                    gv_mma(acc, xv.x, xv.y, buf[j].x, buf[j].y);
+                    gv_mma(acc2, xv.z, xv.w, buf[j].z, buf[j].w);
+                    if (++kk == c.ks_len) {
+                        // acc[0..1] = D[batch g][weight rows 2t, 2t+1] of block rb over this warp's K slice
+                        if (g < NB)
+                            *reinterpret_cast<float2*>(s_part + (((size_t)warp * p.nb_max + rb) * NB + g) * 8 + t * 2) =
+                                make_float2(acc[0] + acc2[0], acc[1] + acc2[1]);
+                        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+                        acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
+                        kk = 0;
+                        ++rb;
                     }
                 }
             }
+        };
+#pragma unroll 1
+        for (int bt = 0; bt < n_batches; bt += 2) {
+            compute(bt, bufA);
+            gv_issue(p, c, bt + 2, lane, bufA);
+            compute(bt + 1, bufB);
+            gv_issue(p, c, bt + 3, lane, bufB);
         }
-        if (g == G - 1) {
-#pragma unroll
-            for (int r = 0; r < GV_R; ++r)
-#pragma unroll
-                for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
-            int r0, r1;
-            item_rows(item, r0, r1);
-            if (swiglu) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (lane == b && b < p.B) {
-                        const float gte = acc[0][b], up = acc[1][b];
-                        const float y = gte / (1.0f + __expf(-gte)) * up;
-                        reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)b * p.ld_out + item] =
-                            __float2bfloat16_rn(y);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < GV_R; ++r) {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        if (lane == r * NB + b && b < p.B) {
-                            const int row = r == 0 ? r0 : r1;
-                            float y = acc[r][b];
-                            if (p.residual != nullptr)
-                                y += __bfloat162float(p.residual[(size_t)b * p.ld_res + row]);
-                            if (p.out_fp32)
-                                reinterpret_cast<float*>(p.out)[(size_t)b * p.ld_out + row] = y;
-                            else
-                                reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)b * p.ld_out + row] =
-                                    __float2bfloat16_rn(y);
-                        }
-                    }
-                }
-            }
-        }
-    };
+    }
+    __syncthreads();
 
-    for (int s = 0; s < total_steps; s += 2) {
-        issue(s + 1, bufB);
-        compute(s, bufA);
-        issue(s + 2, bufA);
-        compute(s + 1, bufB);
+    // ---------------- reduce the 16 K slices (fixed order), epilogue, coalesced writes ----------------
+    {
+        const int nk32 = K >> 5;
+        auto row_value = [&](int rbl, int b, int r) {
+            float v = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < GV_WARPS; ++ww) {
+                const bool has = (nk32 * (ww + 1)) / GV_WARPS > (nk32 * ww) / GV_WARPS;  // K < 512: empty slices
+                if (has) v += s_part[(((size_t)ww * p.nb_max + rbl) * NB + b) * 8 + r];
+            }
+            return v;
+        };
+        if (p.act == ACT_SWIGLU) {
+            for (int idx = tid; idx < c.nu * p.B; idx += GV_THREADS) {
+                const int b = idx / c.nu, r = idx - b * c.nu;
+                const float gt = row_value(r >> 2, b, r & 3);
+                const float up = row_value(r >> 2, b, (r & 3) + 4);
+                reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)b * p.ld_out + c.u_lo + r] =
+                    __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
+            }
+        } else {
+            for (int idx = tid; idx < c.nu * p.B; idx += GV_THREADS) {
+                const int b = idx / c.nu, r = idx - b * c.nu;
+                float y = row_value(r >> 3, b, r & 7);
+                const int row = c.u_lo + r;
+                if (p.residual != nullptr) y += __bfloat162float(p.residual[(size_t)b * p.ld_res + row]);
+                if (p.out_fp32) reinterpret_cast<float*>(p.out)[(size_t)b * p.ld_out + row] = y;
+                else reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)b * p.ld_out + row] = __float2bfloat16_rn(y);
+            }
+        }
     }
 }
 
 template <int NB>
-int launch_gemv(const GemvParams& p, cudaStream_t stream) {
-    const size_t smem = (size_t)NB * p.K * 2;
-    B2_CHECK_ARG(smem <= 200 * 1024 + 24 * 1024, "gemv: activation tile does not fit shared memory (B=%d K=%d)",
-                 p.B, p.K);
+int launch_gemv(GemvParams p, cudaStream_t stream) {
+    const int grid = num_sms();
+    const long long units = p.act == ACT_SWIGLU ? (p.N >> 1) : p.N;
+    const int nu_max = (int)((units + grid - 1) / grid);
+    p.nb_max = p.act == ACT_SWIGLU ? (nu_max + 3) / 4 : (nu_max + 7) / 8;
+    const size_t smem = (size_t)NB * p.K * 2 + (size_t)GV_WARPS * p.nb_max * NB * 8 * 4;
+    B2_CHECK_ARG(smem <= 226 * 1024, "gemv: activation tile + partial table do not fit shared memory (B=%d K=%d N=%d)",
+                 p.B, p.K, p.N);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        B2_CUDA_CHECK(cudaFuncSetAttribute(gemv_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-        attr_smem = smem > 48 * 1024 ? smem : 48 * 1024;
+        const size_t want = smem > 48 * 1024 ? smem : 48 * 1024;
+        B2_CUDA_CHECK(cudaFuncSetAttribute(gemv_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+        attr_smem = want;
     }
-    gemv_kernel<NB><<<num_sms(), GV_THREADS, smem, stream>>>(p);
+    gemv_kernel<NB><<<grid, GV_THREADS, smem, stream>>>(p);
     B2_LAUNCH_CHECK();
     return 0;
 }
 
+size_t gemv_smem_bytes(int B, int N, int K, int act) {
+    const int NB = B == 1 ? 1 : (B == 2 ? 2 : (B <= 4 ? 4 : 8));
+    const int grid = num_sms();
+    const long long units = act == ACT_SWIGLU ? (N >> 1) : N;
+    const int nu_max = (int)((units + grid - 1) / grid);
+    const int nb_max = act == ACT_SWIGLU ? (nu_max + 3) / 4 : (nu_max + 7) / 8;
+    return (size_t)NB * K * 2 + (size_t)GV_WARPS * nb_max * NB * 8 * 4;
+}
+
 }  // namespace
+
+bool gemv_fits(int B, int N, int K, int act) { return B >= 1 && B <= 8 && gemv_smem_bytes(B, N, K, act) <= 226 * 1024; }
 
 int gemv_bf16(const GemvArgs& g, cudaStream_t stream) {
     B2_CHECK_ARG(g.B >= 1 && g.B <= 8, "gemv: batch must be 1..8 (got %d)", g.B);
@@ -249,7 +294,7 @@ int gemv_bf16(const GemvArgs& g, cudaStream_t stream) {
     p.gamma = reinterpret_cast<const __nv_bfloat16*>(g.norm_gamma); p.eps = g.eps;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(g.residual); p.ld_res = g.ld_res;
     p.out = g.out; p.ld_out = g.ld_out; p.out_fp32 = g.out_fp32;
-    p.B = g.B; p.N = g.N; p.K = g.K; p.act = g.act;
+    p.B = g.B; p.N = g.N; p.K = g.K; p.act = g.act; p.nb_max = 0;
     if (g.B == 1) return launch_gemv<1>(p, stream);
     if (g.B == 2) return launch_gemv<2>(p, stream);
     if (g.B <= 4) return launch_gemv<4>(p, stream);

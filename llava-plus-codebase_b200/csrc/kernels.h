@@ -39,6 +39,7 @@ struct GemvArgs {
     int act = ACT_NONE;
 };
 int gemv_bf16(const GemvArgs& g, cudaStream_t stream);
+bool gemv_fits(int B, int N, int K, int act);  // activation tile + partial table fit in shared memory
 
 // ---- norms (norms.cu) ------------------------------------------------------------------------------
 int layernorm_bf16(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,

@@ -348,7 +348,9 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const int h = d.hidden, I = d.inter, H = d.heads, V = d.vocab;
     const int nsplit = decode_nsplit(B, H);
     B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, st));
-    const bool small = B <= 8;
+    // batch <= 8: tensor-core GEMV kernels (falls back to the skinny-M tcgen05 GEMM when the activations do not fit smem)
+    const bool small = B <= 8 && gemv_fits(B, h, I, ACT_NONE) && gemv_fits(B, 2 * I, h, ACT_SWIGLU) &&
+                       gemv_fits(B, 3 * h, h, ACT_NONE) && gemv_fits(B, V, h, ACT_NONE);
     for (int l = 0; l < d.layers; ++l) {
         LlamaLayer& L = m->ll[l];
         if (small) {
@@ -502,8 +504,9 @@ int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     }
     B2_CUDA_CHECK(cudaGraphLaunch(kv->graph, st));
     // kernels per step: embed + L*(qkv, attn, o, gate/up, down [+2 norms when B>8]) + head(+norm) + argmax + 3
-    const int per_layer = B <= 8 ? 5 : 7;
-    g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (B <= 8 ? 1 : 2) + 4;
+    const bool small = B <= 8 && gemv_fits(B, m->d.hidden, m->d.inter, ACT_NONE) && gemv_fits(B, m->d.vocab, m->d.hidden, ACT_NONE);
+    const int per_layer = small ? 5 : 7;
+    g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (small ? 1 : 2) + 4;
     return 0;
 }
 
@@ -891,7 +894,7 @@ int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_le
     if (logits_mode == B2_LOGITS_LAST) {
         // only the last valid position per sample feeds generation (the reference computes lm_head on all S)
         B2_TRY(rmsnorm_gather_bf16(m->x.p, m->last_idx.as<int32_t>(), m->final_norm.p, m->xlast.p, B, h, d.rms_eps, st));
-        if (B <= 8)
+        if (B <= 8 && gemv_fits(B, V, h, ACT_NONE))
             B2_TRY(gemv(m->xlast.p, h, m->lm_head.p, h, nullptr, 0.f, nullptr, 0, logits_out, V, 1, B, V, h, ACT_NONE, st));
         else
             B2_TRY(gemm(m->xlast.p, h, m->lm_head.p, h, nullptr, nullptr, 0, logits_out, V, 1, B, V, h, ACT_NONE, st));
