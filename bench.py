@@ -126,6 +126,9 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference CPU path (oracle port) — bounded sample, extrapolated
 # ---------------------------------------------------------------------------------------------------------
+_CPU_WEIGHTS = {}
+
+
 def pick_cpu_threads(dtype):
     """PyTorch's CPU GEMV/GEMM can get SLOWER with every hardware thread on a many-core host. Probe a decode-shaped
     GEMV and a prefill-shaped GEMM at a few thread counts and keep the fastest (the kinder baseline)."""
@@ -176,10 +179,15 @@ def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=None):
     pick_cpu_threads(dtype)
     cfg = O.make_config(hidden=m["hidden"], inter=m["inter"], layers=sample_layers, heads=m["heads"])
     g = torch.Generator().manual_seed(0)
-    w = {}
-    for key, shape, kind in O.weight_shapes(cfg):
-        t = torch.empty(*shape, dtype=dtype).normal_(0.0, O.init_std(kind, shape), generator=g)
-        w[key] = t + 1.0 if kind == "g" else t
+    key = (m["name"], str(dtype))
+    if _CPU_WEIGHTS.get("key") != key:  # built once per process (max sample_layers = 4 decoder layers)
+        full = O.make_config(hidden=m["hidden"], inter=m["inter"], layers=4, heads=m["heads"])
+        w = {}
+        for k, shape, kind in O.weight_shapes(full):
+            t = torch.empty(*shape, dtype=dtype).normal_(0.0, O.init_std(kind, shape), generator=g)
+            w[k] = t + 1.0 if kind == "g" else t
+        _CPU_WEIGHTS.update(key=key, w=w)
+    w = _CPU_WEIGHTS["w"]
     images = torch.randn(1, 3, 336, 336, generator=g)
     ids = torch.randint(3, VOCAB, (1, S - P_IMG + 1), generator=g)
     ids[0, 5] = IMAGE_TOKEN
@@ -214,6 +222,7 @@ def cpu_reference_sample(m, S, N, sample_layers=4, decode_steps=4, dtype=None):
     t_decode_step = t_dec_0 + per_layer_dec * L
     total = t_enc + t_prefill + (N - 1) * t_decode_step
     return dict(value=(S + N) / total, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
+                dtype="bf16" if dtype == torch.bfloat16 else "f32",
                 sample=(f"oracle port ({str(dtype).replace('torch.', '')} and {torch.get_num_threads()} of {os.cpu_count()} threads: the fastest "
                         f"dtype/thread count probed on this host) at full {m['name']} dims: ViT+projector 1 image in full, "
                         f"{sample_layers} of {L} decoder layers for an S={S} prefill (lm_head on all positions, as the "
@@ -241,7 +250,7 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": "prefill+decode tokens/s", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": last["dtype"], "data": "synthetic",
         "config": workload_config(args, m, S),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": last["cores"], "kind": "port",
                          "sample": last["sample"], "breakdown": last["breakdown"]},
