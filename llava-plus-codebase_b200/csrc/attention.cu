@@ -10,6 +10,8 @@
 //                      cache reads and an in-kernel last-CTA merge (HBM-bound: reads each K/V row once).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -473,6 +475,14 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(DecodeAttnParam
 int flash_attn_bf16(const FlashArgs& a, cudaStream_t stream) {
     B2_CHECK_ARG(a.D == 64 || a.D == 128, "flash_attn: head_dim must be 64 or 128 (got %d)", a.D);
     B2_CHECK_ARG(a.B > 0 && a.H > 0 && a.S > 0, "flash_attn: empty problem");
+    static const bool use_tc = [] {
+        const char* e = getenv("B2_FLASH_TC");
+        return e == nullptr || e[0] != '0';
+    }();
+    return use_tc ? flash_attn_tc_bf16(a, stream) : flash_attn_mma_bf16(a, stream);
+}
+
+int flash_attn_mma_bf16(const FlashArgs& a, cudaStream_t stream) {
     FlashParams p;
     p.q = reinterpret_cast<const __nv_bfloat16*>(a.q); p.q_bs = a.q_bs; p.q_ts = a.q_ts; p.q_hs = a.q_hs;
     p.k = reinterpret_cast<const __nv_bfloat16*>(a.k); p.k_bs = a.k_bs; p.k_ts = a.k_ts; p.k_hs = a.k_hs;

@@ -71,7 +71,9 @@ struct FlashArgs {
     int causal = 0;
     float scale = 1.f;
 };
-int flash_attn_bf16(const FlashArgs& a, cudaStream_t stream);
+int flash_attn_bf16(const FlashArgs& a, cudaStream_t stream);      // dispatcher (tcgen05 unless B2_FLASH_TC=0)
+int flash_attn_tc_bf16(const FlashArgs& a, cudaStream_t stream);   // attention_tc.cu: tcgen05 + TMEM + TMA
+int flash_attn_mma_bf16(const FlashArgs& a, cudaStream_t stream);  // attention.cu: mma.sync variant
 
 // prefill: RoPE on q (in place) and k inside qkv [B*S, 3*H*D]; roped k and v written to the cache
 // kcache/vcache: [Bmax, H, Smax, D] for one layer. Positions are 0..S-1 (right-padded rows).
