@@ -124,6 +124,15 @@ int b2_op_gemm(const void* A, int lda, const void* W, int ldw, const void* bias,
 int b2_op_gemv(const void* x, int64_t ldx, const void* W, int ldw, const void* norm_gamma, float eps,
                const void* residual, int ld_res, void* out, int ld_out, int out_fp32, int B, int N, int K, int act,
                void* stream);
+/* decode Linear at batch 9..128 (swap-AB stream-K tcgen05 GEMM, csrc/gemm_skinny.cu): out[B,N] = x[B,K]·W[N,K]^T
+ * (+ residual); act = B2_ACT_NONE | B2_ACT_SWIGLU (out [B,N/2], W rows block-64 interleaved). `workspace` (fp32,
+ * >= b2_op_gemm_skinny_workspace_bytes) and `counters` (int32, >= b2_op_gemm_skinny_counter_bytes, zero-filled once
+ * by the caller; the kernel leaves them zero) are caller-owned scratch. */
+int b2_op_gemm_skinny(const void* x, int ldx, const void* W, int ldw, const void* residual, int ld_res, void* out,
+                      int ld_out, int out_fp32, int B, int N, int K, int act, void* workspace, int64_t workspace_bytes,
+                      void* counters, void* stream);
+int64_t b2_op_gemm_skinny_workspace_bytes(int B, int N, int K);
+int64_t b2_op_gemm_skinny_counter_bytes(int N);
 int b2_op_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,
                     void* stream);
 int b2_op_rmsnorm(const void* x, const void* gamma, void* y, int rows, int cols, float eps, void* stream);

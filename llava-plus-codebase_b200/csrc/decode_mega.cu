@@ -41,8 +41,13 @@ constexpr int MK_TILE_BYTES = 8 * MK_ROW_STRIDE;
 constexpr int MK_MAXNB = 32;                  // max 8-row blocks per CTA per phase (host-checked)
 constexpr int MK_MAXL = 48;                   // decoder layers whose weight-pointer table is cached in smem
 constexpr int MK_MAX_STAGES = 12;
-constexpr int MK_L2_AHEAD = 0;                // optional L2 bulk prefetch beyond the ring while the producer is stalled. MEASURED
-                                              // HARMFUL on B200 (8 tiles: 4.18 vs 2.81 ms/token; unconditional 16 tiles: 3.24) -> off
+// L2 look-ahead (MegaParams::l2_ahead tiles, l2_mode): the producer that issues the ring load of tile t also pulls
+// tile t + l2_ahead of its own sequence into L2, so the 126 MB L2 extends the ring: HBM keeps streaming for
+// (stages + l2_ahead) tiles while the consumers sit in a dependency, and the ring refills from L2 hits afterwards.
+//   mode 1: prefetch.global.L2 per 128 B line from the LSU (does not queue in front of the TMA ring loads)
+//   mode 2: cp.async.bulk.prefetch.L2 per row piece (TMA queue). The first implementation issued these only while
+//           stalled on a full ring and was MEASURED HARMFUL (8 tiles: 4.18 vs 2.81 ms/token; every tile, 16 ahead:
+//           3.24): the ring loads queue behind the prefetches in the TMA engine.
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
@@ -201,6 +206,108 @@ __device__ __forceinline__ void mk_prologue(const PhaseIO& c, int K, int B, floa
         }
     }
     cons_sync();
+}
+
+// Single-pass variant (MegaParams::fast_prologue): every load of the phase's activation vector is issued before the
+// first use (one L2 round trip instead of one per loop iteration), the RMSNorm weights arrive in registers (`gpre`,
+// loaded BEFORE the grid barrier: they do not depend on activations), and each thread sums the 16 warp partials
+// itself (one CTA barrier fewer). Same summation order -> bit-identical to mk_prologue. Needs K/8 <= 2*MK_CONS when
+// gamma is set (the caller checks).
+template <int NB>
+__device__ __forceinline__ void mk_prologue_fast(const PhaseIO& c, int K, float eps, int tid, int lane, int warp,
+                                                 __nv_bfloat16* xs, float (*s_red)[NB], const uint4 (&gpre)[2]) {
+    const int nvec = K >> 3;
+    if (c.gamma == nullptr) {
+        constexpr int J = 3;
+        for (int i0 = 0; i0 < nvec; i0 += J * MK_CONS) {
+            uint4 u[NB][J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int idx = i0 + j * MK_CONS + tid;
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+                    u[b][j] = idx < nvec ? ldcg16(c.xin + (size_t)b * K + idx * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int idx = i0 + j * MK_CONS + tid;
+                if (idx < nvec) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) *reinterpret_cast<uint4*>(xs + (size_t)b * K + idx * 8) = u[b][j];
+                }
+            }
+        }
+        cons_sync();
+        return;
+    }
+    uint4 u[NB][2];
+    float ss[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = j * MK_CONS + tid;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+            u[b][j] = idx < nvec ? ldcg16(c.xin + (size_t)b * K + idx * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float f[8];
+            unpack8(u[b][j], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss[b] += f[e] * f[e];
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float v = warp_sum(ss[b]);
+        if (lane == 0) s_red[warp][b] = v;
+    }
+    cons_sync();
+    float rstd[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < MK_CONS_WARPS; ++i) t += s_red[i][b];
+        rstd[b] = rsqrtf(t / K + eps);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = j * MK_CONS + tid;
+        if (idx < nvec) {
+            float gf[8];
+            unpack8(gpre[j], gf);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float f[8], o[8];
+                unpack8(u[b][j], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = gf[e] * round_bf16(f[e] * rstd[b]);
+                *reinterpret_cast<uint4*>(xs + (size_t)b * K + idx * 8) =
+                    make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+        }
+    }
+    cons_sync();  // xs complete; also orders the s_red reads above before the next phase's writes
+}
+
+// RMSNorm weights of GEMV phase `ph` into registers (independent of activations: issued before the grid barrier)
+__device__ __forceinline__ bool mk_gamma_preload(const MegaParams& p, const MegaLayer* layers, int ph, int n_phases,
+                                                 int tid, uint4 (&gpre)[2]) {
+    if (ph >= n_phases || mk_is_attention(p, ph)) return false;
+    const PhaseIO io = mk_phase_io(p, layers, ph);
+    const int nvec = p.h >> 3;  // every normed phase has K = h
+    if (io.gamma == nullptr || nvec > 2 * MK_CONS) return false;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = j * MK_CONS + tid;
+        gpre[j] = idx < nvec ? __ldg(reinterpret_cast<const uint4*>(io.gamma) + idx) : make_uint4(0, 0, 0, 0);
+    }
+    return true;
 }
 
 __device__ __forceinline__ void mk_mma(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
@@ -445,6 +552,9 @@ __device__ __forceinline__ void cursor_next(TileCursor& t, const MegaParams& p, 
     ++t.ph;
     cursor_seek(t, p, layers, n_phases);
 }
+__device__ __forceinline__ void prefetch_l2_line(const void* gsrc) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
@@ -488,43 +598,41 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
 
     if (warp >= MK_CONS_WARPS) {
         // =========================== PRODUCERS: stream every phase's weight tiles, in order ===========================
-        // `cp` feeds the shared-memory ring with TMA bulk copies, throttled by free ring slots. While a producer
-        // warp is stalled on a full ring (the consumers sit in a barrier / prologue / attention), it spends the idle
-        // time issuing bulk L2 prefetches for its own tiles just BEYOND the ring (`pf`, at most MK_L2_AHEAD tiles
-        // further), so HBM keeps streaming into the 126 MB L2 during the dependency and the ring refills from L2
-        // afterwards. (Prefetching unconditionally for every tile doubled the TMA issue work and was 5% slower.)
+        // `cp` feeds the shared-memory ring with TMA bulk copies, throttled by free ring slots; `pf` runs l2_ahead
+        // tiles in front of it and only touches L2 (see the note at MK_L2 above).
         const uint32_t pw = (uint32_t)(warp - MK_CONS_WARPS);
+        const uint32_t ahead = (uint32_t)p.l2_ahead;  // multiple of MK_PROD_WARPS: pf stays in this warp's residue class
         TileCursor cp, pf;
         cursor_begin(cp, p, s_layers, n_phases);
         cursor_begin(pf, p, s_layers, n_phases);
         while (cp.valid) {
             if (cp.tile % (uint32_t)MK_PROD_WARPS == pw) {
+                if (ahead != 0) {
+                    // L2 look-ahead first, so it is already in flight while this warp waits for a free ring slot
+                    while (pf.valid && pf.tile < cp.tile + ahead) cursor_next(pf, p, s_layers, n_phases);
+                    if (pf.valid) {
+                        const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
+                        if (p.l2_mode == 2) {
+                            bool pvalid;
+                            const int pfrow = mk_phys_row(pf.c, pf.rb, lane & 7, pvalid);
+                            if (lane < 8 && pvalid)
+                                bulk_prefetch_l2(pf.c.W + (size_t)pfrow * pf.c.K + (size_t)pf.kc * MK_KT, pbytes);
+                        } else {
+                            bool pvalid;  // 4 lanes per row, 128 B lines dealt round-robin
+                            const int pfrow = mk_phys_row(pf.c, pf.rb, lane >> 2, pvalid);
+                            if (pvalid) {
+                                const char* base = reinterpret_cast<const char*>(pf.c.W + (size_t)pfrow * pf.c.K +
+                                                                                 (size_t)pf.kc * MK_KT);
+                                for (uint32_t off = (uint32_t)(lane & 3) * 128u; off < pbytes; off += 512u)
+                                    prefetch_l2_line(base + off);
+                            }
+                        }
+                    }
+                }
                 const uint32_t stage = cp.tile % (uint32_t)n_stages;
                 const uint32_t parity = (cp.tile / (uint32_t)n_stages) & 1u;
                 const uint32_t row_bytes = (uint32_t)min(MK_KT, cp.c.K - cp.kc * MK_KT) * 2u;
-                if (MK_L2_AHEAD > 0) {
-                    // keep pf on this warp's first tile beyond the ring
-                    while (pf.valid && (pf.tile < cp.tile + (uint32_t)n_stages || pf.tile % (uint32_t)MK_PROD_WARPS != pw))
-                        cursor_next(pf, p, s_layers, n_phases);
-                    uint32_t spins = 0;
-                    for (;;) {
-                        uint32_t ready = 0;
-                        if (lane == 0) ready = mbar_try_wait(&empty_bar[stage], parity ^ 1u);
-                        ready = __shfl_sync(0xffffffffu, ready, 0);
-                        if (ready) break;
-                        if (pf.valid && pf.tile < cp.tile + (uint32_t)n_stages + (uint32_t)MK_L2_AHEAD) {
-                            bool pvalid;
-                            const int pfrow = mk_phys_row(pf.c, pf.rb, lane & 7, pvalid);
-                            if (lane < 8 && pvalid) {
-                                const uint32_t pbytes = (uint32_t)min(MK_KT, pf.c.K - pf.kc * MK_KT) * 2u;
-                                bulk_prefetch_l2(pf.c.W + (size_t)pfrow * pf.c.K + (size_t)pf.kc * MK_KT, pbytes);
-                            }
-                            for (int i = 0; i < MK_PROD_WARPS && pf.valid; ++i) cursor_next(pf, p, s_layers, n_phases);
-                        }
-                        if (++spins > (1u << 24)) asm volatile("trap;");
-                    }
-                    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)mk_rows_in_block(cp.c, cp.rb) * row_bytes);
-                } else if (lane == 0) {
+                if (lane == 0) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);  // slot drained by all consumer warps
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)mk_rows_in_block(cp.c, cp.rb) * row_bytes);
                 }
@@ -557,6 +665,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
         uint4* dst = reinterpret_cast<uint4*>(p.x + (size_t)blockIdx.x * p.h);
         for (int i = tid; i < p.h / 8; i += MK_CONS) dst[i] = src[i];
     }
+    uint4 gpre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    bool gpre_ok = p.fast_prologue != 0 && mk_gamma_preload(p, s_layers, 0, n_phases, tid, gpre);
     unsigned int bar_target = p.bar_base + gridDim.x;
     grid_sync(p.bar_count, bar_target);
 
@@ -579,7 +689,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                 const int b = tid / c.nu, r = tid - b * c.nu;
                 res_pref = __bfloat162float(__ldcg(io.residual + (size_t)b * io.ld_out + (size_t)c.u_lo + r));
             }
-            mk_prologue<NB>(io, c.K, B, p.eps, tid, lane, warp, xs, s_red, s_rstd);
+            if (p.fast_prologue != 0 && (io.gamma == nullptr || gpre_ok))
+                mk_prologue_fast<NB>(io, c.K, p.eps, tid, lane, warp, xs, s_red, gpre);
+            else
+                mk_prologue<NB>(io, c.K, B, p.eps, tid, lane, warp, xs, s_red, s_rstd);
             if (tracing) p.trace[ph * 4 + 1] = clock64();
 #pragma unroll 1
             for (int rb = 0; rb < c.nb; ++rb) {
@@ -613,6 +726,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
             mk_epilogue<NB>(p, s_layers, ph, c, B, tid, s_gpart, res_pref, have_res);
         }
         if (tracing) p.trace[ph * 4 + 3] = clock64();
+        gpre_ok = p.fast_prologue != 0 && mk_gamma_preload(p, s_layers, ph + 1, n_phases, tid, gpre);
         bar_target += gridDim.x;
         grid_sync(p.bar_count, bar_target);
     }

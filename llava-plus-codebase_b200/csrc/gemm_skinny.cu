@@ -1,0 +1,315 @@
+// Weight-streaming "skinny" GEMM for decode at batch 9..128 on sm_100a (swap-AB + stream-K):
+//
+//     out[b, n] = sum_k x[b, k] * W[n, k]   (+ residual[b, n])          b < B <= 128,  n < N
+//     out[b, c] = silu(gate_c . x_b) * (up_c . x_b)                     (ACT_SWIGLU, W rows block-64 interleaved)
+//
+// A decode step at these batch sizes is still a pure weight stream (every weight byte is used by <= 128 tokens),
+// so the kernel is organised around HBM, not around the tensor pipe:
+//   * swap-AB: the WEIGHT tile is the 128-row M operand of tcgen05.mma (128 x BN x 16, fp32 accumulators in TMEM),
+//     the activations are the narrow N operand (BN = 32/64/128 >= B, rows >= B zero-filled by TMA) — no M padding
+//     of the batch to 128 and no wasted weight re-reads.
+//   * stream-K: the (weight tile, k-block) space is cut into gridDim.x contiguous ranges that differ by at most one
+//     16 KB k-block, so every SM streams the same number of weight bytes whatever N and K are (N = 4096 gives only
+//     32 tiles for 148 SMs). A tile that is shared by several CTAs is reduced through an fp32 workspace by the LAST
+//     CTA to arrive, in fixed slot order (deterministic), which then runs the fused epilogue.
+//   * warp-specialised: 1 TMA producer thread (deep smem ring, ~200 KB in flight per SM), 1 MMA thread, 4 epilogue
+//     warps (tcgen05.ld -> transposed, coalesced stores: lane = weight row, consecutive lanes = consecutive n).
+// Replaces, for B > 8, the HF one-token Linear calls (transformers modeling_llama.py:251-289 q/k/v/o_proj, :182-184
+// LlamaMLP, :486-487 lm_head) behind the reference's decode branch (llava/model/llava_arch.py:103-112).
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2 {
+
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+namespace {
+
+constexpr int SK_BM = 128;          // weight rows per tile (UMMA M)
+constexpr int SK_BK = 64;           // 64 bf16 = one 128 B swizzle row
+constexpr int SK_THREADS = 192;     // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue (TMEM lane quadrant = warp % 4)
+constexpr int SK_W_TILE = SK_BM * SK_BK * 2;
+
+template <int BN>
+struct SkCfg {
+    static constexpr int X_TILE = BN * SK_BK * 2;
+    static constexpr int STAGE = SK_W_TILE + X_TILE;
+    static constexpr int STAGES = BN == 32 ? 10 : (BN == 64 ? 8 : 6);
+    static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 64 / 128 / 256: powers of two
+    static constexpr int UP_BYTES = 64 * 33 * 4;  // SwiGLU staging of the tile's up rows, one 32-column chunk
+    static constexpr int SMEM = STAGES * STAGE + UP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct SkEpi {
+    const __nv_bfloat16* residual;  // [B, ld_res] or nullptr (may alias out)
+    void* out;                      // bf16 / fp32 [B, ld_out]
+    float* partial;                 // stream-K workspace: [tile][maxseg][BN][128] fp32
+    int* counters;                  // [tiles], zero-initialised, self-resetting
+    int ld_out, ld_res, out_fp32, maxseg;
+};
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// CTA that owns global k-block unit u when `total` units are cut into `grid` ranges [total*c/grid, total*(c+1)/grid)
+__device__ __forceinline__ int sk_cta_of(long long u, long long total, int grid) {
+    int c = (int)((u * grid) / total);
+    while (c + 1 < grid && (total * (c + 1)) / grid <= u) ++c;
+    while (c > 0 && (total * c) / grid > u) --c;
+    return c;
+}
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, int N, int K,
+                   int B, SkEpi ep) {
+    using Cfg = SkCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t sk_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    float* s_up = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::UP_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (N + SK_BM - 1) / SK_BM;
+    const int nkb = (K + SK_BK - 1) / SK_BK;
+    const long long total = (long long)num_m * nkb;
+    const int grid = gridDim.x;
+    const long long u0 = (total * blockIdx.x) / grid;
+    const long long u1 = (total * (blockIdx.x + 1)) / grid;
+    const int t_first = (int)(u0 / nkb), t_last = (int)((u1 - 1) / nkb);  // u1 > u0: the host keeps grid <= total
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer: weights are read exactly once -> evict-first; activations stay in L2 =====
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_first; t <= t_last; ++t) {
+                const int kb0 = (int)(max(u0, (long long)t * nkb) - (long long)t * nkb);
+                const int kb1 = (int)(min(u1, (long long)(t + 1) * nkb) - (long long)t * nkb);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sw = smem + stage * Cfg::STAGE;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
+                    tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * SK_BK, t * SK_BM, kEvictFirst);
+                    tma_load_2d(sw + SK_W_TILE, &tmap_x, &full_bar[stage], kb * SK_BK, 0, kEvictLast);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_bf16_f32(SK_BM, BN);
+            int stage = 0; uint32_t phase = 0; int local = 0;
+            for (int t = t_first; t <= t_last; ++t, ++local) {
+                const int kb0 = (int)(max(u0, (long long)t * nkb) - (long long)t * nkb);
+                const int kb1 = (int)(min(u1, (long long)(t + 1) * nkb) - (long long)t * nkb);
+                const int as = local & 1;
+                mbar_wait(&tmem_empty[as], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sw = smem_u32(smem + stage * Cfg::STAGE);
+                    const uint64_t da = make_sw128_kmajor_desc(sw);
+                    const uint64_t db = make_sw128_kmajor_desc(sw + SK_W_TILE);
+#pragma unroll
+                    for (int k = 0; k < SK_BK / 16; ++k)
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 =====
+        const int q = warp & 3;               // TMEM lane quadrant
+        const int row_in_tile = q * 32 + lane;
+        const int et = threadIdx.x - 64;      // 0..127
+        int local = 0;
+        for (int t = t_first; t <= t_last; ++t, ++local) {
+            const int as = local & 1;
+            mbar_wait(&tmem_full[as], (local >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const int first = sk_cta_of((long long)t * nkb, total, grid);
+            const int last = sk_cta_of((long long)(t + 1) * nkb - 1, total, grid);
+            const int nseg = last - first + 1;
+            const int seg = (int)blockIdx.x - first;
+            float* slot0 = ep.partial + (size_t)t * ep.maxseg * (BN * SK_BM);
+            bool finalize = true;
+            if (nseg > 1) {
+                float* mine = slot0 + (size_t)seg * (BN * SK_BM);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mine[(size_t)(c * 32 + j) * SK_BM + row_in_tile] = __uint_as_float(v[j]);
+                }
+                __threadfence();
+                epi_sync();
+                if (et == 0) *s_flag = (atomicAdd(&ep.counters[t], 1) == nseg - 1) ? 1 : 0;
+                epi_sync();
+                finalize = *s_flag != 0;
+                if (finalize) __threadfence();
+            }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                if (!finalize) break;  // CTA-uniform: the last CTA to arrive owns the tile's epilogue
+                float acc[32];
+                if (nseg == 1) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+                } else if (finalize) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                    for (int sidx = 0; sidx < nseg; ++sidx) {  // fixed order: deterministic whatever CTA arrives last
+                        const float* ps = slot0 + (size_t)sidx * (BN * SK_BM) + (size_t)(c * 32) * SK_BM + row_in_tile;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] += __ldcg(ps + (size_t)j * SK_BM);
+                    }
+                }
+                if constexpr (ACT == ACT_SWIGLU) {
+                    // tile rows [0,64) = gate, [64,128) = up of channels t*64 + (0..63): up rows go through smem
+                    if (finalize && q >= 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) s_up[((q - 2) * 32 + lane) * 33 + j] = acc[j];
+                    }
+                    epi_sync();
+                    if (finalize && q < 2) {
+                        const int ch = t * 64 + q * 32 + lane;
+                        if (ch < N / 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int b = c * 32 + j;
+                                if (b < B) {
+                                    const float g = acc[j], u = s_up[(q * 32 + lane) * 33 + j];
+                                    reinterpret_cast<__nv_bfloat16*>(ep.out)[(size_t)b * ep.ld_out + ch] =
+                                        __float2bfloat16_rn(__fdividef(g, 1.0f + __expf(-g)) * u);
+                                }
+                            }
+                        }
+                    }
+                    epi_sync();
+                } else {
+                    const int n = t * SK_BM + row_in_tile;
+                    if (n < N) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int b = c * 32 + j;
+                            if (b < B) {
+                                float y = acc[j];
+                                if (ep.residual != nullptr) y += __bfloat162float(ep.residual[(size_t)b * ep.ld_res + n]);
+                                if (ep.out_fp32) reinterpret_cast<float*>(ep.out)[(size_t)b * ep.ld_out + n] = y;
+                                else reinterpret_cast<__nv_bfloat16*>(ep.out)[(size_t)b * ep.ld_out + n] = __float2bfloat16_rn(y);
+                            }
+                        }
+                    }
+                }
+            }
+            if (nseg > 1 && finalize && et == 0) ep.counters[t] = 0;  // ready for the next launch
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+struct SkPlan { int bn, num_m, nkb, grid, maxseg; long long total; };
+
+SkPlan sk_plan(int B, int N, int K) {
+    SkPlan p;
+    p.bn = B <= 32 ? 32 : (B <= 64 ? 64 : 128);
+    p.num_m = (N + SK_BM - 1) / SK_BM;
+    p.nkb = (K + SK_BK - 1) / SK_BK;
+    p.total = (long long)p.num_m * p.nkb;
+    p.grid = (long long)num_sms() < p.total ? num_sms() : (int)p.total;
+    const long long per_min = p.total / p.grid;  // >= 1
+    p.maxseg = (int)((p.nkb + per_min - 1) / per_min) + 1;
+    return p;
+}
+
+template <int BN, int ACT>
+int sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkPlan& pl, int N, int K, int B, const SkEpi& ep,
+              cudaStream_t st) {
+    using Cfg = SkCfg<BN>;
+    static bool attr_set = false;
+    auto kern = gemm_skinny_kernel<BN, ACT>;
+    if (!attr_set) {
+        B2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set = true;
+    }
+    kern<<<pl.grid, SK_THREADS, Cfg::SMEM, st>>>(tw, tx, N, K, B, ep);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+size_t gemm_skinny_workspace_bytes(int B, int N, int K) {
+    const SkPlan p = sk_plan(B, N, K);
+    return (size_t)p.num_m * p.maxseg * p.bn * SK_BM * sizeof(float);
+}
+size_t gemm_skinny_counter_bytes(int N) { return (size_t)((N + SK_BM - 1) / SK_BM) * sizeof(int); }
+
+int gemm_skinny_bf16(const SkinnyArgs& g, cudaStream_t stream) {
+    B2_CHECK_ARG(g.B >= 1 && g.B <= 128 && g.N > 0 && g.K > 0, "gemm_skinny: bad problem B=%d N=%d K=%d", g.B, g.N, g.K);
+    B2_CHECK_ARG(g.K % 8 == 0, "gemm_skinny: K must be a multiple of 8 (K=%d)", g.K);
+    B2_CHECK_ARG(g.act == ACT_NONE || g.act == ACT_SWIGLU, "gemm_skinny: unsupported activation %d", g.act);
+    B2_CHECK_ARG(g.act != ACT_SWIGLU || (g.N % 128 == 0 && !g.out_fp32 && g.residual == nullptr),
+                 "gemm_skinny: swiglu needs N %% 128 == 0, bf16 output, no residual (N=%d)", g.N);
+    B2_CHECK_ARG(g.partial != nullptr && g.counters != nullptr, "gemm_skinny: workspace missing");
+    const SkPlan pl = sk_plan(g.B, g.N, g.K);
+    B2_CHECK_ARG(g.partial_bytes >= gemm_skinny_workspace_bytes(g.B, g.N, g.K),
+                 "gemm_skinny: workspace too small (%zu < %zu)", g.partial_bytes, gemm_skinny_workspace_bytes(g.B, g.N, g.K));
+    CUtensorMap tw, tx;
+    B2_TRY(make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, SK_BM));
+    B2_TRY(make_tmap_bf16(&tx, g.x, g.B, g.K, g.ldx, pl.bn));
+    SkEpi ep;
+    ep.residual = reinterpret_cast<const __nv_bfloat16*>(g.residual);
+    ep.out = g.out; ep.partial = g.partial; ep.counters = g.counters;
+    ep.ld_out = g.ld_out; ep.ld_res = g.ld_res; ep.out_fp32 = g.out_fp32; ep.maxseg = pl.maxseg;
+    const bool sw = g.act == ACT_SWIGLU;
+    switch (pl.bn) {
+        case 32: return sw ? sk_launch<32, ACT_SWIGLU>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
+                           : sk_launch<32, ACT_NONE>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
+        case 64: return sw ? sk_launch<64, ACT_SWIGLU>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
+                           : sk_launch<64, ACT_NONE>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
+        default: return sw ? sk_launch<128, ACT_SWIGLU>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
+                           : sk_launch<128, ACT_NONE>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
+    }
+}
+
+}  // namespace b2

@@ -27,6 +27,22 @@ struct GemmArgs {
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 
+// ---- swap-AB stream-K GEMM for decode at batch 9..128 (gemm_skinny.cu) ------------------------------------
+// out[B, N] = x[B,K] · W[N,K]^T (+ residual); ACT_SWIGLU: out[B, N/2] (W rows block-64 interleaved).
+struct SkinnyArgs {
+    const void* x = nullptr; int ldx = 0;        // bf16 [B, K]
+    const void* W = nullptr; int ldw = 0;        // bf16 [N, K]
+    const void* residual = nullptr; int ld_res = 0;  // bf16 [B, N] or null (may alias out)
+    void* out = nullptr; int ld_out = 0; int out_fp32 = 0;
+    int B = 0, N = 0, K = 0;
+    int act = ACT_NONE;                          // ACT_NONE | ACT_SWIGLU
+    float* partial = nullptr; size_t partial_bytes = 0;  // >= gemm_skinny_workspace_bytes(B, N, K)
+    int* counters = nullptr;                     // >= gemm_skinny_counter_bytes(N), zero-initialised once
+};
+int gemm_skinny_bf16(const SkinnyArgs& g, cudaStream_t stream);
+size_t gemm_skinny_workspace_bytes(int B, int N, int K);
+size_t gemm_skinny_counter_bytes(int N);
+
 // ---- weight-streaming GEMV for decode (gemv.cu) ---------------------------------------------------
 // out[B, N] = (rmsnorm(x) or x)[B,K] · W[N,K]^T (+ residual); B <= 8. ACT_SWIGLU: out[B, N/2].
 struct GemvArgs {
@@ -111,6 +127,9 @@ struct MegaParams {
     unsigned int *bar_count = nullptr, *done_count = nullptr;  // zero-initialised
     unsigned int bar_base = 0;  // barrier-counter value before this launch = launches so far * (5L+2) * grid
     float eps = 1e-5f, theta = 10000.f, scale_log2 = 1.f;
+    int l2_ahead = 0;       // weight tiles pulled into L2 in front of the shared-memory ring (0 = off), multiple of 4
+    int l2_mode = 1;        // 1 = prefetch.global.L2 lines (LSU), 2 = cp.async.bulk.prefetch.L2 (TMA queue)
+    int fast_prologue = 0;  // single-pass activation staging with pre-barrier RMSNorm-weight loads
     long long* trace = nullptr;  // optional [n_phases+2][4] SM-clock timestamps of CTA 0 (B2_MEGA_TRACE=1)
 };
 // one launch = embed -> all layers -> lm_head -> argmax -> token store; cur_len/step_counter advance on device

@@ -93,6 +93,7 @@ struct b2_kv {
     int max_batch = 0, max_seq = 0;
     DevBuf k, v;  // [L][B][H][Smax][D]
     DevBuf len_dev, tok, step_counter, out_tokens, attn_partial, attn_counters;
+    DevBuf sk_partial, sk_counters;  // stream-K workspace of the skinny decode GEMM (batch 9..128)
     std::vector<int32_t> len_host;
     int out_capacity = 0;  // steps
     // cached decode-step graph
@@ -181,6 +182,22 @@ int gemv(const void* x, int64_t ldx, const void* W, int ldw, const void* gamma, 
     g.ld_res = ld_res; g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.B = B; g.N = N; g.K = K;
     g.act = act;
     return gemv_bf16(g, st);
+}
+
+// decode Linear at batch 9..128: swap-AB stream-K tcgen05 GEMM over the kv-owned workspace
+int skinny(b2_kv* kv, const void* x, int ldx, const void* W, int ldw, const void* res, int ld_res, void* out, int ld_out,
+           int out_fp32, int B, int N, int K, int act, cudaStream_t st) {
+    SkinnyArgs g;
+    g.x = x; g.ldx = ldx; g.W = W; g.ldw = ldw; g.residual = res; g.ld_res = ld_res;
+    g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.B = B; g.N = N; g.K = K; g.act = act;
+    g.partial = kv->sk_partial.as<float>(); g.partial_bytes = kv->sk_partial.bytes;
+    g.counters = kv->sk_counters.as<int>();
+    return gemm_skinny_bf16(g, st);
+}
+bool use_skinny(const b2_kv* kv, int B) {
+    if (B <= 8 || B > 128 || kv->sk_partial.p == nullptr) return false;
+    const char* e = getenv("B2_DECODE_SKINNY");
+    return !(e != nullptr && e[0] == '0');
 }
 
 int decode_nsplit(int B, int H) {
@@ -351,11 +368,15 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     // batch <= 8: tensor-core GEMV kernels (falls back to the skinny-M tcgen05 GEMM when the activations do not fit smem)
     const bool small = B <= 8 && gemv_fits(B, h, I, ACT_NONE) && gemv_fits(B, 2 * I, h, ACT_SWIGLU) &&
                        gemv_fits(B, 3 * h, h, ACT_NONE) && gemv_fits(B, V, h, ACT_NONE);
+    const bool sk = !small && use_skinny(kv, B);  // batch 9..128: swap-AB stream-K GEMM (weights streamed once, all SMs)
     for (int l = 0; l < d.layers; ++l) {
         LlamaLayer& L = m->ll[l];
         if (small) {
             B2_TRY(gemv(m->x.p, h, L.wqkv.p, h, L.ln1.p, d.rms_eps, nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h,
                         ACT_NONE, st));
+        } else if (sk) {
+            B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln1.p, m->xn.p, B, h, d.rms_eps, st));
+            B2_TRY(skinny(kv, m->xn.p, h, L.wqkv.p, h, nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h, ACT_NONE, st));
         } else {
             B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln1.p, m->xn.p, B, h, d.rms_eps, st));
             B2_TRY(gemm(m->xn.p, h, L.wqkv.p, h, nullptr, nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h, ACT_NONE, st));
@@ -377,6 +398,11 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
             B2_TRY(gemv(m->x.p, h, L.wgu.p, h, L.ln2.p, d.rms_eps, nullptr, 0, m->act.p, I, 0, B, 2 * I, h,
                         ACT_SWIGLU, st));
             B2_TRY(gemv(m->act.p, I, L.wd.p, I, nullptr, 0.f, m->x.p, h, m->x.p, h, 0, B, h, I, ACT_NONE, st));
+        } else if (sk) {
+            B2_TRY(skinny(kv, m->attn.p, h, L.wo.p, h, m->x.p, h, m->x.p, h, 0, B, h, h, ACT_NONE, st));
+            B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln2.p, m->xn.p, B, h, d.rms_eps, st));
+            B2_TRY(skinny(kv, m->xn.p, h, L.wgu.p, h, nullptr, 0, m->act.p, I, 0, B, 2 * I, h, ACT_SWIGLU, st));
+            B2_TRY(skinny(kv, m->act.p, I, L.wd.p, I, m->x.p, h, m->x.p, h, 0, B, h, I, ACT_NONE, st));
         } else {
             B2_TRY(gemm(m->attn.p, h, L.wo.p, h, nullptr, m->x.p, h, m->x.p, h, 0, B, h, h, ACT_NONE, st));
             B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln2.p, m->xn.p, B, h, d.rms_eps, st));
@@ -387,6 +413,9 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     if (small) {
         B2_TRY(gemv(m->x.p, h, m->lm_head.p, h, m->final_norm.p, d.rms_eps, nullptr, 0, m->logits.p, V, 1, B, V, h,
                     ACT_NONE, st));
+    } else if (sk) {
+        B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, B, h, d.rms_eps, st));
+        B2_TRY(skinny(kv, m->xn.p, h, m->lm_head.p, h, nullptr, 0, m->logits.p, V, 1, B, V, h, ACT_NONE, st));
     } else {
         B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, B, h, d.rms_eps, st));
         B2_TRY(gemm(m->xn.p, h, m->lm_head.p, h, nullptr, nullptr, 0, m->logits.p, V, 1, B, V, h, ACT_NONE, st));
@@ -429,6 +458,10 @@ bool use_mega(const b2_model* m, int B) {
     return flag == 1;
 }
 
+// defaults of the megakernel knobs (measured on B200: profiles/r1e_mega_sweep.txt)
+constexpr int kMegaL2AheadDefault = 0;
+constexpr int kMegaFastPrologueDefault = 0;
+
 int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const b2_model_desc& d = m->d;
     MegaParams p;
@@ -448,6 +481,15 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     kv->mega_bar_base += (unsigned int)(5 * d.layers + 2) * (unsigned int)num_sms();
     p.eps = d.rms_eps; p.theta = d.rope_theta;
     p.scale_log2 = (1.0f / sqrtf((float)m->hd)) * 1.4426950408889634f;
+    {   // tuning knobs, re-read every launch so a sweep can flip them inside one process (scripts/mega_sweep.py)
+        const char* e = getenv("B2_MEGA_L2_AHEAD");
+        int ahead = e ? atoi(e) : kMegaL2AheadDefault;
+        p.l2_ahead = ahead < 0 ? 0 : (ahead > 64 ? 64 : ahead) / 4 * 4;
+        e = getenv("B2_MEGA_L2_MODE");
+        p.l2_mode = (e && e[0] == '2') ? 2 : 1;
+        e = getenv("B2_MEGA_FAST_PROLOGUE");
+        p.fast_prologue = e ? (e[0] != '0') : kMegaFastPrologueDefault;
+    }
     static int trace_mode = -1;
     if (trace_mode < 0) { const char* e = getenv("B2_MEGA_TRACE"); trace_mode = (e && e[0] == '1') ? 1 : 0; }
     if (trace_mode == 1) {
@@ -751,6 +793,22 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
         b2_kv_destroy(kv);
         return r;
     }
+    if (max_batch > 8 && max_batch <= 128) {
+        const int h = m->d.hidden, I = m->d.inter, V = m->d.vocab;
+        size_t ws = 0;
+        const int shapes[5][2] = {{3 * h, h}, {h, h}, {2 * I, h}, {h, I}, {V, h}};
+        int nmax = 0;
+        for (auto& sh : shapes) {
+            const size_t b = gemm_skinny_workspace_bytes(max_batch, sh[0], sh[1]);
+            ws = b > ws ? b : ws;
+            nmax = sh[0] > nmax ? sh[0] : nmax;
+        }
+        if ((r = kv->sk_partial.alloc(ws)) != 0 || (r = kv->sk_counters.alloc(gemm_skinny_counter_bytes(nmax))) != 0) {
+            b2_kv_destroy(kv);
+            return r;
+        }
+        cudaMemset(kv->sk_counters.p, 0, gemm_skinny_counter_bytes(nmax));
+    }
     cudaMemset(kv->k.p, 0, per);
     cudaMemset(kv->v.p, 0, per);
     cudaMemset(kv->len_dev.p, 0, (size_t)max_batch * 4);
@@ -781,7 +839,7 @@ int b2_kv_destroy(b2_kv* kv) {
     if (kv->ev_fork) cudaEventDestroy(kv->ev_fork);
     if (kv->ev_join) cudaEventDestroy(kv->ev_join);
     DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
-                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync};
+                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters};
     for (DevBuf* b : bs) b->free();
     delete kv;
     return 0;
@@ -989,6 +1047,23 @@ int b2_op_gemv(const void* x, int64_t ldx, const void* W, int ldw, const void* n
     return gemv(x, ldx, W, ldw, norm_gamma, eps, residual, ld_res, out, ld_out, out_fp32, B, N, K, act,
                 reinterpret_cast<cudaStream_t>(stream));
 }
+
+int b2_op_gemm_skinny(const void* x, int ldx, const void* W, int ldw, const void* residual, int ld_res, void* out,
+                      int ld_out, int out_fp32, int B, int N, int K, int act, void* workspace, int64_t workspace_bytes,
+                      void* counters, void* stream) {
+    B2_CHECK_ARG(x && W && out && workspace && counters, "b2_op_gemm_skinny: null argument");
+    SkinnyArgs g;
+    g.x = x; g.ldx = ldx; g.W = W; g.ldw = ldw; g.residual = residual; g.ld_res = ld_res;
+    g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.B = B; g.N = N; g.K = K; g.act = act;
+    g.partial = reinterpret_cast<float*>(workspace); g.partial_bytes = (size_t)workspace_bytes;
+    g.counters = reinterpret_cast<int*>(counters);
+    return gemm_skinny_bf16(g, reinterpret_cast<cudaStream_t>(stream));
+}
+int64_t b2_op_gemm_skinny_workspace_bytes(int B, int N, int K) {
+    if (B < 1 || B > 128 || N < 1 || K < 1) return -1;
+    return (int64_t)gemm_skinny_workspace_bytes(B, N, K);
+}
+int64_t b2_op_gemm_skinny_counter_bytes(int N) { return N < 1 ? -1 : (int64_t)gemm_skinny_counter_bytes(N); }
 
 int b2_op_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,
                     void* stream) {

@@ -60,6 +60,9 @@ SIGNATURES = {
     "b2_argmax": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "b2_op_gemm": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b2_op_gemv": (_i32, [_vp, _i64, _vp, _i32, _vp, _f32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b2_op_gemm_skinny": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "b2_op_gemm_skinny_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "b2_op_gemm_skinny_counter_bytes": (_i64, [_i32]),
     "b2_op_layernorm": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "b2_op_rmsnorm": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "b2_op_flash_attn": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),

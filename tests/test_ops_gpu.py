@@ -129,6 +129,91 @@ def test_gemm_linearity_and_determinism():
     assert torch.equal(gemm(A1, W, out_fp32=True), c1)
 
 
+# ------------------------------------------------------------------------- skinny (swap-AB stream-K) GEMM
+def skinny(x, W, residual=None, act=_b2.ACT_NONE, out_fp32=False, out=None, scratch=None):
+    B, K = x.shape
+    N = W.shape[0]
+    lib = _b2.load_library()
+    n_out = N // 2 if act == _b2.ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty(B, n_out, device=DEV, dtype=torch.float32 if out_fp32 else BF)
+    if scratch is None:
+        ws = torch.empty(int(lib.b2_op_gemm_skinny_workspace_bytes(B, N, K)) // 4, device=DEV, dtype=torch.float32)
+        cnt = torch.zeros(int(lib.b2_op_gemm_skinny_counter_bytes(N)) // 4, device=DEV, dtype=torch.int32)
+    else:
+        ws, cnt = scratch
+    _b2.check(lib.b2_op_gemm_skinny(P(x), x.stride(0), P(W), W.stride(0), P(residual),
+                                    residual.stride(0) if residual is not None else 0, P(out), out.stride(0),
+                                    int(out_fp32), B, N, K, act, P(ws), ws.numel() * 4, P(cnt), S()), "b2_op_gemm_skinny")
+    assert int(cnt.abs().sum()) == 0, "stream-K tile counters must be left at zero"
+    return out
+
+
+@pytest.mark.parametrize("B,N,K", [
+    (32, 128, 64),          # one tile, one k-block, one CTA
+    (32, 256, 1024),        # 2 tiles x 16 k-blocks over 32 CTAs: every tile split 16 ways
+    (9, 4096, 4096),        # 7B o_proj: 32 tiles on 148 SMs (stream-K splits each tile ~4.6 ways)
+    (32, 12288, 4096),      # 7B fused QKV
+    (32, 4096, 11008),      # 7B down_proj (K = 172 k-blocks)
+    (17, 5120, 13824),      # 13B down_proj, ragged batch
+    (33, 4096, 4096),       # BN = 64 variant
+    (64, 15360, 5120),      # 13B QKV at bs 64
+    (100, 4096, 4096),      # BN = 128 variant, ragged batch
+    (20, 200, 264),         # ragged N (not a tile multiple) and K tail (264 = 4*64 + 8)
+])
+def test_gemm_skinny_plain(B, N, K):
+    x, W = rnd(B, K), rnd(N, K, scale=K ** -0.5)
+    assert_close(skinny(x, W), ref_linear(x, W))
+
+
+def test_gemm_skinny_residual_inplace_and_fp32_logits():
+    B, N, K = 32, 4096, 11008
+    x, W, r = rnd(B, K), rnd(N, K, scale=K ** -0.5), rnd(B, N)
+    want = ref_linear(x, W) + r.float()
+    assert_close(skinny(x, W, residual=r), want)
+    r2 = r.clone()
+    skinny(x, W, residual=r2, out=r2)  # out aliases residual, as the decoder layers use it
+    assert_close(r2, want)
+    x, W = rnd(32, 4096), rnd(32000, 4096, scale=1 / 64)  # lm_head: 250 tiles, fp32 logits
+    torch.testing.assert_close(skinny(x, W, out_fp32=True), ref_linear(x, W), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("B,I,h", [(32, 11008, 4096), (12, 512, 256), (64, 13824, 5120), (128, 1024, 512)])
+def test_gemm_skinny_swiglu(B, I, h):
+    x, Wg, Wu = rnd(B, h), rnd(I, h, scale=h ** -0.5), rnd(I, h, scale=h ** -0.5)
+    Wgu = torch.empty(2 * I, h, device=DEV, dtype=BF)
+    lib = _b2.load_library()
+    _b2.check(lib.b2_op_interleave_gate_up(P(Wg), P(Wu), P(Wgu), I, h, S()))
+    want = torch.nn.functional.silu(ref_linear(x, Wg)) * ref_linear(x, Wu)
+    assert_close(skinny(x, Wgu, act=_b2.ACT_SWIGLU), want)
+
+
+def test_gemm_skinny_matches_tile_gemm_and_is_deterministic():
+    """Same operands through the prefill GEMM (batch as M) and the decode GEMM (batch as N): fp32 outputs agree to
+    accumulation-order noise; the stream-K reduction is bitwise repeatable (fixed slot order) with reused scratch."""
+    x, W = rnd(32, 4096), rnd(12288, 4096, scale=1 / 64)
+    lib = _b2.load_library()
+    ws = torch.empty(int(lib.b2_op_gemm_skinny_workspace_bytes(32, 12288, 4096)) // 4, device=DEV, dtype=torch.float32)
+    cnt = torch.zeros(int(lib.b2_op_gemm_skinny_counter_bytes(12288)) // 4, device=DEV, dtype=torch.int32)
+    a = skinny(x, W, out_fp32=True, scratch=(ws, cnt))
+    for _ in range(3):
+        assert torch.equal(skinny(x, W, out_fp32=True, scratch=(ws, cnt)), a)
+    torch.testing.assert_close(a, gemm(x, W, out_fp32=True), rtol=1e-3, atol=1e-3)
+
+
+def test_gemm_skinny_rejects_bad_arguments():
+    lib = _b2.load_library()
+    x, W = rnd(200, 64), rnd(128, 64)
+    assert lib.b2_op_gemm_skinny_workspace_bytes(200, 128, 64) == -1
+    ws, cnt = torch.empty(1 << 20, device=DEV), torch.zeros(64, device=DEV, dtype=torch.int32)
+    with pytest.raises(ValueError):
+        skinny(x, W, scratch=(ws, cnt))  # B > 128
+    with pytest.raises(ValueError):
+        skinny(rnd(16, 60), rnd(128, 60), scratch=(ws, cnt))  # K % 8 != 0
+    with pytest.raises(ValueError):
+        skinny(rnd(16, 64), rnd(128, 64), scratch=(ws[:16], cnt))  # workspace too small
+
+
 def test_gemm_rejects_bad_arguments():
     A, W = rnd(16, 60), rnd(16, 60)
     with pytest.raises(ValueError):
