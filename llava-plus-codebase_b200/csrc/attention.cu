@@ -257,31 +257,50 @@ __device__ __forceinline__ float rope_apply(float x, float partner_signed, float
     return round_bf16(round_bf16(x * c) + round_bf16(partner_signed * s));
 }
 
-// grid: (B*S), block: H*D/2/… one thread per (head, i<D/2) pair
-__global__ void rope_kv_write_kernel(__nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
-                                     __nv_bfloat16* __restrict__ vcache, int S, int H, int D, int Smax,
-                                     float theta) {
+// grid: (B*S) tokens, 256 threads. The D/2 (cos, sin) pairs of the token's position are tabulated once in shared
+// memory (they are the same for every head); every thread then moves 16-byte vectors: one (head, 8-lane chunk) item
+// = q/k/v elements [c*8, c*8+8) and their rotation partners [D/2 + c*8, ...), six loads and six stores of 16 B.
+__global__ void __launch_bounds__(256)
+rope_kv_write_kernel(__nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
+                     __nv_bfloat16* __restrict__ vcache, int S, int H, int D, int Smax, float theta) {
+    __shared__ float s_c[128], s_s[128];  // D/2 <= 128
     const int row = blockIdx.x;  // b*S + t
     const int b = row / S, t = row % S;
     const int hd = H * D;
+    const int half = D / 2;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) rope_cos_sin(t, i, D, theta, s_c[i], s_s[i]);
+    __syncthreads();
     __nv_bfloat16* q = qkv + (size_t)row * 3 * hd;
     __nv_bfloat16* k = q + hd;
     const __nv_bfloat16* v = q + 2 * hd;
-    const int half = D / 2;
-    for (int idx = threadIdx.x; idx < H * half; idx += blockDim.x) {
-        const int h = idx / half, i = idx % half;
-        float c, s;
-        rope_cos_sin(t, i, D, theta, c, s);
-        const int o1 = h * D + i, o2 = o1 + half;
-        const float q1 = __bfloat162float(q[o1]), q2 = __bfloat162float(q[o2]);
-        const float k1 = __bfloat162float(k[o1]), k2 = __bfloat162float(k[o2]);
-        q[o1] = __float2bfloat16_rn(rope_apply(q1, -q2, c, s));
-        q[o2] = __float2bfloat16_rn(rope_apply(q2, q1, c, s));
-        const size_t co = (((size_t)b * H + h) * Smax + t) * D;
-        kcache[co + i] = __float2bfloat16_rn(rope_apply(k1, -k2, c, s));
-        kcache[co + i + half] = __float2bfloat16_rn(rope_apply(k2, k1, c, s));
-        vcache[co + i] = v[o1];
-        vcache[co + i + half] = v[o2];
+    const int cpd = half / 8;  // 8-element chunks per half head
+    for (int idx = threadIdx.x; idx < H * cpd; idx += blockDim.x) {
+        const int h = idx / cpd, c = idx % cpd;
+        const int o1 = h * D + c * 8, o2 = o1 + half;
+        const uint4 q1 = *reinterpret_cast<const uint4*>(q + o1), q2 = *reinterpret_cast<const uint4*>(q + o2);
+        const uint4 k1 = *reinterpret_cast<const uint4*>(k + o1), k2 = *reinterpret_cast<const uint4*>(k + o2);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(v + o1), v2 = *reinterpret_cast<const uint4*>(v + o2);
+        const uint32_t qa[4] = {q1.x, q1.y, q1.z, q1.w}, qb[4] = {q2.x, q2.y, q2.z, q2.w};
+        const uint32_t ka[4] = {k1.x, k1.y, k1.z, k1.w}, kb[4] = {k2.x, k2.y, k2.z, k2.w};
+        uint32_t oq1[4], oq2[4], ok1[4], ok2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float c0 = s_c[c * 8 + 2 * e], s0 = s_s[c * 8 + 2 * e];
+            const float c1 = s_c[c * 8 + 2 * e + 1], s1 = s_s[c * 8 + 2 * e + 1];
+            const float qa0 = bf16_lo(qa[e]), qa1 = bf16_hi(qa[e]), qb0 = bf16_lo(qb[e]), qb1 = bf16_hi(qb[e]);
+            const float ka0 = bf16_lo(ka[e]), ka1 = bf16_hi(ka[e]), kb0 = bf16_lo(kb[e]), kb1 = bf16_hi(kb[e]);
+            oq1[e] = pack_bf16(rope_apply(qa0, -qb0, c0, s0), rope_apply(qa1, -qb1, c1, s1));
+            oq2[e] = pack_bf16(rope_apply(qb0, qa0, c0, s0), rope_apply(qb1, qa1, c1, s1));
+            ok1[e] = pack_bf16(rope_apply(ka0, -kb0, c0, s0), rope_apply(ka1, -kb1, c1, s1));
+            ok2[e] = pack_bf16(rope_apply(kb0, ka0, c0, s0), rope_apply(kb1, ka1, c1, s1));
+        }
+        *reinterpret_cast<uint4*>(q + o1) = make_uint4(oq1[0], oq1[1], oq1[2], oq1[3]);
+        *reinterpret_cast<uint4*>(q + o2) = make_uint4(oq2[0], oq2[1], oq2[2], oq2[3]);
+        const size_t co = (((size_t)b * H + h) * Smax + t) * D + c * 8;
+        *reinterpret_cast<uint4*>(kcache + co) = make_uint4(ok1[0], ok1[1], ok1[2], ok1[3]);
+        *reinterpret_cast<uint4*>(kcache + co + half) = make_uint4(ok2[0], ok2[1], ok2[2], ok2[3]);
+        *reinterpret_cast<uint4*>(vcache + co) = v1;
+        *reinterpret_cast<uint4*>(vcache + co + half) = v2;
     }
 }
 
@@ -475,10 +494,9 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(DecodeAttnParam
 int flash_attn_bf16(const FlashArgs& a, cudaStream_t stream) {
     B2_CHECK_ARG(a.D == 64 || a.D == 128, "flash_attn: head_dim must be 64 or 128 (got %d)", a.D);
     B2_CHECK_ARG(a.B > 0 && a.H > 0 && a.S > 0, "flash_attn: empty problem");
-    static const bool use_tc = [] {
-        const char* e = getenv("B2_FLASH_TC");
-        return e == nullptr || e[0] != '0';
-    }();
+    // tcgen05 kernel unless B2_FLASH_TC=0 selects the mma.sync one (A/B knob, re-read per call: scripts/attn_bench.py)
+    const char* e = getenv("B2_FLASH_TC");
+    const bool use_tc = e == nullptr || e[0] != '0';
     return use_tc ? flash_attn_tc_bf16(a, stream) : flash_attn_mma_bf16(a, stream);
 }
 
@@ -516,7 +534,9 @@ int flash_attn_mma_bf16(const FlashArgs& a, cudaStream_t stream) {
 int rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, int D, int Smax, float theta,
                   cudaStream_t stream) {
     B2_CHECK_ARG(S <= Smax, "rope_kv_write: S=%d exceeds cache capacity %d", S, Smax);
-    B2_CHECK_ARG(D % 2 == 0, "rope_kv_write: odd head_dim");
+    B2_CHECK_ARG(D % 16 == 0 && D <= 256, "rope_kv_write: head_dim must be a multiple of 16, <= 256 (got %d)", D);
+    B2_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(kcache) |
+                   reinterpret_cast<uintptr_t>(vcache)) & 15) == 0, "rope_kv_write: buffers must be 16-byte aligned");
     rope_kv_write_kernel<<<B * S, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(qkv),
                                                     reinterpret_cast<__nv_bfloat16*>(kcache),
                                                     reinterpret_cast<__nv_bfloat16*>(vcache), S, H, D, Smax, theta);

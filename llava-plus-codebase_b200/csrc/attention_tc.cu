@@ -5,18 +5,22 @@
 // (transformers modeling_llama.py:199-221 eager_attention_forward; modeling_clip.py:261-279).
 //
 // CTA = one (batch, head, 128-query tile); 192 threads:
-//   warp 0 / lane 0 : TMA producer — Q once, then K_j / V_j tiles (128 keys) into a 2-stage ring
+//   warp 0 / lane 0 : TMA producer — Q once, then K_j / V_j tiles (128 keys) into separate rings (K: 2 stages; V: 2
+//                     stages at d=128, 1 at d=64 so that TWO CTAs fit one SM: one CTA's exp2-bound softmax overlaps
+//                     the other's MMAs; at d=64 a 128x128 tile costs 1024 clk of MUFU but only 512 clk of tensor pipe)
 //                     (4-D tensor maps over the strided [b, t, h, d] views: the same kernel reads the fused qkv
 //                     activation buffer of the ViT and the [B, H, Smax, 128] KV cache of the decoder)
 //   warp 1 / lane 0 : MMA issuer — S = Q K_j^T  (UMMA 128x128xD, both operands K-major, SWIZZLE_128B)
 //                                  O += P_j V_j (UMMA 128xDx128; P from smem K-major, V straight from its
 //                                  [keys, d] tile as an MN-major operand — no transpose pass)
-//   warps 2..5      : softmax — thread r owns query row r: tcgen05.ld S row, scale/mask, running max / sum,
-//                     rescale O in TMEM (tcgen05.ld / tcgen05.st) when the max moved, write P (bf16) into the
-//                     swizzled smem operand tile, finally O / l -> global.
-// mbarriers: q_full, kv_full[2], kv_empty[2], s_full, p_full, o_done.
+//   warps 2..5      : softmax — thread r owns query row r: tcgen05.ld the S row, scale/mask, running max / sum, write
+//                     P = exp2(s - m) (bf16) into the swizzled smem operand tile; O in TMEM is rescaled only when a
+//                     row's max grew by more than 2^8 (lazy rescale: P and l keep using the stale max, which cancels
+//                     in O / l), finally O / l -> global.
+// mbarriers: q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, p_full, o_done.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -72,8 +76,15 @@ struct FlashTcParams {
     float scale_log2;
 };
 
-template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int D>
+struct TcCfg {
+    static constexpr int VS = D == 64 ? 1 : 2;
+    static constexpr int MIN_CTAS = D == 64 ? 2 : 1;
+    static constexpr int SMEM = (3 + VS) * TC_BN * D * 2 + TC_BM * TC_BN * 2 + 1024 /*align*/ + 128 /*barriers*/;
+};
+
+template <int D, bool CAUSAL, int MIN_CTAS>
+__global__ void __launch_bounds__(TC_THREADS, MIN_CTAS)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, FlashTcParams p) {
     constexpr int SLABS = D / 64;                 // 64-wide (128 B) slabs of the head dim
@@ -84,18 +95,21 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     extern __shared__ uint8_t tc_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    constexpr int VS = TcCfg<D>::VS;          // V ring stages
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;            // [2][TILE_BYTES]
-    uint8_t* sV = sK + 2 * TILE_BYTES;        // [2][TILE_BYTES]
-    uint8_t* sP = sV + 2 * TILE_BYTES;
+    uint8_t* sV = sK + 2 * TILE_BYTES;        // [VS][TILE_BYTES]
+    uint8_t* sP = sV + VS * TILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;   // [2]
-    uint64_t* kv_empty = bars + 3;  // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* o_done = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_done = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * TC_BM;
@@ -109,7 +123,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v);
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+        }
         mbar_init(s_full, 1);
         mbar_init(p_full, 4);  // one arrive per softmax warp
         mbar_init(o_done, 1);
@@ -131,13 +148,15 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_arrive_expect_tx(q_full, TILE_BYTES);
             for (int sl = 0; sl < SLABS; ++sl) tma_load_4d(sQ + sl * SLAB_BYTES, &tm_q, q_full, sl * 64, q0, head, b);
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-                for (int sl = 0; sl < SLABS; ++sl) {
-                    tma_load_4d(sK + s * TILE_BYTES + sl * SLAB_BYTES, &tm_k, &kv_full[s], sl * 64, j * TC_BN, head, b);
-                    tma_load_4d(sV + s * TILE_BYTES + sl * SLAB_BYTES, &tm_v, &kv_full[s], sl * 64, j * TC_BN, head, b);
-                }
+                const int ks = j & 1, vs = j % VS;
+                mbar_wait(&k_empty[ks], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+                for (int sl = 0; sl < SLABS; ++sl)
+                    tma_load_4d(sK + ks * TILE_BYTES + sl * SLAB_BYTES, &tm_k, &k_full[ks], sl * 64, j * TC_BN, head, b);
+                mbar_wait(&v_empty[vs], ((j / VS) & 1) ^ 1);
+                mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+                for (int sl = 0; sl < SLABS; ++sl)
+                    tma_load_4d(sV + vs * TILE_BYTES + sl * SLAB_BYTES, &tm_v, &v_full[vs], sl * 64, j * TC_BN, head, b);
             }
         }
     } else if (warp == 1) {
@@ -147,8 +166,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             constexpr uint32_t idesc_o = make_idesc(TC_BM, D, 1);
             mbar_wait(q_full, 0);
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_full[s], (j >> 1) & 1);
+                const int s = j & 1, vs = j % VS;
+                mbar_wait(&k_full[s], (j >> 1) & 1);
                 tc_fence_after();
                 // S = Q K_j^T : K-loop over the head dim in steps of 16 (32 B inside a 128 B swizzle row; slabs of 64)
 #pragma unroll
@@ -157,8 +176,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_bf16(tmem_S, make_sw128_kmajor_desc(smem_u32(sQ) + off),
                               make_sw128_kmajor_desc(smem_u32(sK + s * TILE_BYTES) + off), idesc_s, k != 0 ? 1u : 0u);
                 }
+                umma_commit(&k_empty[s]);  // K_j consumed once S_j is complete
                 umma_commit(s_full);
                 // O += P_j V_j once the softmax warps have written P_j (and rescaled O)
+                mbar_wait(&v_full[vs], (j / VS) & 1);
                 mbar_wait(p_full, j & 1);
                 tc_fence_after();
 #pragma unroll
@@ -166,10 +187,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const uint32_t poff = (k >> 2) * (TC_BM * 128) + (k & 3) * 32;   // P: K-major, 2 slabs of 64 keys
                     const uint32_t voff = k * 16 * 128;                               // V: MN-major, 16 key rows per step
                     umma_bf16(tmem_O, make_sw128_kmajor_desc(smem_u32(sP) + poff),
-                              make_sw128_mnmajor_desc(smem_u32(sV + s * TILE_BYTES) + voff, SLAB_BYTES), idesc_o,
+                              make_sw128_mnmajor_desc(smem_u32(sV + vs * TILE_BYTES) + voff, SLAB_BYTES), idesc_o,
                               (j | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(&kv_empty[s]);  // K_j / V_j (and P_j) consumed
+                umma_commit(&v_empty[vs]);  // V_j (and P_j) consumed
                 umma_commit(o_done);
             }
         }
@@ -184,6 +205,9 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const int key0 = j * TC_BN;
+            // one pass: the scaled, masked score row lives in registers (the d=64 variant runs 2 CTAs/SM under a 168-
+            // register cap and spills part of it to L1-resident local memory; a second tcgen05.ld pass over S instead
+            // was measured 30% slower: profiles/r1e_attn_tc_v2_twopass_2cta_SLOWER.txt)
             float sc[TC_BN];
             float mx = -INFINITY;
 #pragma unroll
@@ -202,9 +226,12 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     mx = fmaxf(mx, x);
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
+            // lazy rescale: keep the stale max while the new one is < 2^8 above it (P <= 256: exact enough in bf16 / fp32;
+            // the stale max cancels in O / l)
+            const bool grow = mx > m_run + 8.0f;  // also true on the first valid tile (m_run = -inf)
+            const float m_new = grow ? mx : m_run;
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            const float corr = exp2f(m_run - m_use);  // m_run = -inf -> 0
+            const float corr = grow ? exp2f(m_run - m_use) : 1.0f;  // m_run = -inf -> 0
             // rescale the running output (in TMEM) once the previous P·V has landed
             if (j > 0) {
                 mbar_wait(o_done, (j - 1) & 1);
@@ -315,7 +342,7 @@ int make_tmap_4d(CUtensorMap* map, const void* ptr, int D, int S, int H, int B, 
     return 0;
 }
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, int MIN_CTAS>
 int launch_tc(const FlashArgs& a, cudaStream_t stream) {
     CUtensorMap tq, tk, tv;
     B2_TRY(make_tmap_4d(&tq, a.q, D, a.S, a.H, a.B, a.q_ts, a.q_hs, a.q_bs));
@@ -327,9 +354,9 @@ int launch_tc(const FlashArgs& a, cudaStream_t stream) {
     p.o_bs = a.o_bs; p.o_ts = a.o_ts; p.o_hs = a.o_hs;
     p.S = a.S;
     p.scale_log2 = a.scale * 1.4426950408889634f;
-    constexpr int smem = 5 * TC_BN * D * 2 + TC_BM * TC_BN * 2 + 1024 + 256;
+    constexpr int smem = TcCfg<D>::SMEM;
     static bool attr_set = false;
-    auto kern = flash_tc_kernel<D, CAUSAL>;
+    auto kern = flash_tc_kernel<D, CAUSAL, MIN_CTAS>;
     if (!attr_set) {
         B2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
@@ -346,8 +373,19 @@ int flash_attn_tc_bf16(const FlashArgs& a, cudaStream_t stream) {
     B2_CHECK_ARG(a.D == 64 || a.D == 128, "flash_attn(tc): head_dim must be 64 or 128 (got %d)", a.D);
     B2_CHECK_ARG((a.o_ts % 8) == 0 && (a.o_hs % 8) == 0 && (a.o_bs % 8) == 0 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0,
                  "flash_attn(tc): output must be 16B aligned with 16B-multiple strides");
-    if (a.D == 64) return a.causal ? launch_tc<64, true>(a, stream) : launch_tc<64, false>(a, stream);
-    return a.causal ? launch_tc<128, true>(a, stream) : launch_tc<128, false>(a, stream);
+    if (a.D == 64) {
+        // d=64: the smem/TMEM/register budget admits two CTAs per SM (168-register cap, part of the score row spills):
+        // one CTA's exp2-bound softmax overlaps the other's MMAs, +26% at B=32 (224.6 vs 178.6 TFLOP/s), but a grid that
+        // does not even fill the SMs once (B=1: 80 CTAs) only pays for the spills (21.2 vs 16.8 us) -> one-CTA build.
+        // B2_FLASH_TC_CTAS=1|2 forces a build (scripts/attn_bench.py; profiles/r1e_attn_tc_v3_lazy_rescale_1v2cta.txt).
+        const char* e = getenv("B2_FLASH_TC_CTAS");
+        const long long ctas = (long long)((a.S + TC_BM - 1) / TC_BM) * a.H * a.B;
+        const bool one = e != nullptr ? e[0] == '1' : ctas <= num_sms();
+        if (one)
+            return a.causal ? launch_tc<64, true, 1>(a, stream) : launch_tc<64, false, 1>(a, stream);
+        return a.causal ? launch_tc<64, true, 2>(a, stream) : launch_tc<64, false, 2>(a, stream);
+    }
+    return a.causal ? launch_tc<128, true, 1>(a, stream) : launch_tc<128, false, 1>(a, stream);
 }
 
 }  // namespace b2

@@ -84,8 +84,9 @@ template <int BN>
 struct GemmCfg {
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 7 : 9);
-    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 7 : 9));
+    static constexpr int ACC_STRIDE = (BN == 192) ? 256 : BN;      // TMEM columns between the two accumulator stages
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;               // power of two (128 / 256 / 512)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -195,7 +196,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 const uint32_t aphase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
                     tc_fence_after();
@@ -227,7 +228,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_after();
             const int row = m_blk * BM + q * 32 + lane;
             const bool row_ok = row < M;
-            const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 
             if constexpr (ACT == ACT_SWIGLU) {
                 // W rows are block-interleaved: within each 128-col group, cols [0,64) = gate, [64,128) = up
@@ -379,16 +380,26 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                      ((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ld_res % 8) == 0),
                  "gemm: residual must be 16B aligned with ld_res %% 8 == 0");
 
-    // Tile-N choice (measured, profiles/r1b_gemm_sweep.json): BN=256 feeds the tensor pipe best (96 B/clk of smem
-    // operand traffic vs 128 B/clk at BN=128, the smem limit) and wins whenever it still yields >= ~0.55 waves of
-    // tiles; smaller tiles only for problems that would otherwise leave most SMs idle.
+    // Tile-N choice. Cost model fitted to profiles/r1b_gemm_sweep.json: a tile costs ~BN / rel(BN) (rel = tensor-pipe
+    // feed efficiency of the shape: BN=256 needs 96 B/clk of smem operand traffic, BN=128 sits on the 128 B/clk limit,
+    // BN=64 is far over it) and the launch takes ceil(tiles / #SMs) waves. BN=192 exists for the N=4096 projections of a
+    // B=1 prefill (M=704): 96 tiles of 256 leave a third of the SMs idle, 132 tiles of 192 fill one wave.
     const int num_m = (g.M + BM - 1) / BM;
-    const int want = (num_sms() * 55) / 100;
     int bn = 64;
-    if (num_m * ((g.N + 255) / 256) >= want) bn = 256;
-    else if (num_m * ((g.N + 127) / 128) >= want) bn = 128;
-    if (g.bn_override == 64 || g.bn_override == 128 || g.bn_override == 256) bn = g.bn_override;
-    if (g.act == ACT_SWIGLU && bn < 128) bn = 128;
+    {
+        const int cand[4] = {256, 192, 128, 64};
+        const float rel[4] = {1.00f, 0.93f, 0.81f, 0.44f};
+        float best = 0.f;
+        for (int i = 0; i < 4; ++i) {
+            if (g.act == ACT_SWIGLU && cand[i] % 128 != 0) continue;
+            const long long tiles = (long long)num_m * ((g.N + cand[i] - 1) / cand[i]);
+            const long long waves = (tiles + num_sms() - 1) / num_sms();
+            const float cost = (float)waves * ((float)cand[i] / rel[i] + 24.f /*per-tile fixed cost*/);
+            if (best == 0.f || cost < best) { best = cost; bn = cand[i]; }
+        }
+    }
+    if (g.bn_override == 64 || g.bn_override == 128 || g.bn_override == 192 || g.bn_override == 256) bn = g.bn_override;
+    if (g.act == ACT_SWIGLU && bn % 128 != 0) bn = 128;
 
     CUtensorMap ta, tb;
     B2_TRY(make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BM));
@@ -406,6 +417,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
         return launch_gemm<128, ACT_SWIGLU>(ta, tb, g.M, g.N, g.K, ep, stream);
     }
     if (bn == 64) return dispatch_act<64>(g.act, ta, tb, g.M, g.N, g.K, ep, stream);
+    if (bn == 192) return dispatch_act<192>(g.act, ta, tb, g.M, g.N, g.K, ep, stream);
     if (bn == 256) return dispatch_act<256>(g.act, ta, tb, g.M, g.N, g.K, ep, stream);
     return dispatch_act<128>(g.act, ta, tb, g.M, g.N, g.K, ep, stream);
 }

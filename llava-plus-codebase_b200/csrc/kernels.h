@@ -23,7 +23,7 @@ struct GemmArgs {
     void* out = nullptr; int ld_out = 0; int out_fp32 = 0;
     int M = 0, N = 0, K = 0;
     int act = ACT_NONE;
-    int bn_override = 0;  // 0 = heuristic, else 64/128/256
+    int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 

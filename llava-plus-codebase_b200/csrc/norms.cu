@@ -103,6 +103,58 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_row_stride, const 
     }
 }
 
+// One CTA (256 threads) per row, single pass with the row in registers: used when there are too few rows for the
+// warp-per-row kernel to fill the machine (a B=1 prefill has 704 rows; one warp walking a 4096-wide row is a chain of
+// dependent L2 round trips: 11 us measured for 11 MB of traffic). Same arithmetic and rounding points as rmsnorm_kernel;
+// cols % 8 == 0, cols <= 8192.
+__global__ void __launch_bounds__(256)
+rmsnorm_row_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_row_stride, const int32_t* __restrict__ row_index,
+                   const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ y, int cols, float eps) {
+    __shared__ float s_part[8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const int64_t src_row = row_index != nullptr ? (int64_t)row_index[row] : (int64_t)row;
+    const __nv_bfloat16* xr = x + src_row * x_row_stride;
+    const int nvec = cols >> 3;
+    uint4 u[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = j * 256 + tid;
+        u[j] = i < nvec ? *reinterpret_cast<const uint4*>(xr + i * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float v[8] = {bf16_lo(u[j].x), bf16_hi(u[j].x), bf16_lo(u[j].y), bf16_hi(u[j].y),
+                            bf16_lo(u[j].z), bf16_hi(u[j].z), bf16_lo(u[j].w), bf16_hi(u[j].w)};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) s_part[tid >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_part[w];
+    const float rstd = rsqrtf(tot / cols + eps);
+    __nv_bfloat16* yr = y + (size_t)row * cols;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = j * 256 + tid;
+        if (i < nvec) {
+            const uint4 g = *reinterpret_cast<const uint4*>(gamma + i * 8);
+            const float v[8] = {bf16_lo(u[j].x), bf16_hi(u[j].x), bf16_lo(u[j].y), bf16_hi(u[j].y),
+                                bf16_lo(u[j].z), bf16_hi(u[j].z), bf16_lo(u[j].w), bf16_hi(u[j].w)};
+            const float gg[8] = {bf16_lo(g.x), bf16_hi(g.x), bf16_lo(g.y), bf16_hi(g.y),
+                                 bf16_lo(g.z), bf16_hi(g.z), bf16_lo(g.w), bf16_hi(g.w)};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = gg[e] * round_bf16(v[e] * rstd);
+            *reinterpret_cast<uint4*>(yr + i * 8) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                               pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+    }
+}
+
 }  // namespace
 
 int layernorm_bf16(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,
@@ -121,6 +173,13 @@ static int rmsnorm_launch(const void* x, int64_t stride, const int32_t* row_inde
                           int rows, int cols, float eps, cudaStream_t stream) {
     B2_CHECK_ARG(rows > 0 && cols > 0 && cols % 256 == 0,
                  "rmsnorm: cols must be a multiple of 256 (cols=%d rows=%d)", cols, rows);
+    if (rows < 4096 && cols <= 8192) {  // few rows: a CTA per row keeps every SM busy and the row in registers
+        rmsnorm_row_kernel<<<rows, 256, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), stride, row_index,
+            reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<__nv_bfloat16*>(y), cols, eps);
+        B2_LAUNCH_CHECK();
+        return 0;
+    }
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     rmsnorm_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), stride, row_index,

@@ -1,4 +1,4 @@
-"""Time b2_op_flash_attn (C-ABI) on the path's attention shapes. Run twice: B2_FLASH_TC=1 (tcgen05) / 0 (mma.sync).
+"""Time b2_op_flash_attn (C-ABI) on the path's attention shapes, every kernel variant in one process (env knobs are re-read per call).
 
     python scripts/attn_bench.py            # prints one line per shape: us, TFLOP/s, max-abs-diff vs torch fp32
 """
@@ -22,8 +22,11 @@ def main():
     lib = _b2.load_library()
     _b2.check(lib.b2_init(0))
     dev = torch.device("cuda:0")
-    tag = "tcgen05" if os.environ.get("B2_FLASH_TC", "1") != "0" else "mma.sync"
-    for (B, S, H, D, causal) in SHAPES:
+    variants = [("tcgen05 2cta/SM@d64", "1", "2"), ("tcgen05 1cta/SM", "1", "1"), ("mma.sync", "0", "1")]
+    for (tag, tc, ctas), (B, S, H, D, causal) in [(v, sh) for sh in SHAPES for v in variants]:
+        if ctas == "1" and tc == "1" and D != 64:
+            continue  # d=128 has a single tcgen05 build
+        os.environ["B2_FLASH_TC"], os.environ["B2_FLASH_TC_CTAS"] = tc, ctas
         g = torch.Generator(device=dev).manual_seed(1)
         q, k, v = (torch.randn(B, S, H, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
         o = torch.empty_like(q)

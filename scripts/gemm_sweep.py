@@ -19,7 +19,8 @@ SHAPES = [  # (name, M, N, K, act)
     ("ViT b1 qkv", 577, 3072, 1024, 0), ("ViT b1 fc1", 577, 4096, 1024, 1), ("ViT b1 fc2", 577, 1024, 4096, 0),
     ("ViT b16 qkv", 9232, 3072, 1024, 0), ("ViT b16 fc1", 9232, 4096, 1024, 1), ("ViT b16 fc2", 9232, 1024, 4096, 0),
     ("ViT b16 out", 9232, 1024, 1024, 0), ("square 8192", 8192, 8192, 8192, 0),
-    ("13B prefill gate/up", 704, 27648, 5120, 3), ("decode B=32 qkv", 32, 12288, 4096, 0),
+    ("13B prefill gate/up", 704, 27648, 5120, 3), ("13B prefill o", 704, 5120, 5120, 0),
+    ("projector fc1 b1", 576, 4096, 1024, 2), ("projector fc2 b1", 576, 4096, 4096, 0),
 ]
 res = []
 for name, M, N, K, act in SHAPES:
@@ -29,8 +30,8 @@ for name, M, N, K, act in SHAPES:
     bias = torch.zeros(N, device=dev, dtype=torch.bfloat16) if act == 1 else None
     out = torch.empty(M, N // 2 if act == 3 else N, device=dev, dtype=torch.bfloat16)
     row = {"shape": name, "M": M, "N": N, "K": K}
-    for bn in (64, 128, 256):
-        if act == 3 and bn == 64:
+    for bn in (64, 128, 192, 256):
+        if act == 3 and bn % 128 != 0:
             continue
         def run(i):
             W = Ws[i % ncopy]

@@ -308,8 +308,38 @@ def test_13b_layer_shapes_decode_equals_prefill_recompute(B):
     eng.close()
 
 
+@pytest.mark.parametrize("B,dims", [(12, (4096, 11008, 32)), (32, (4096, 11008, 32)), (32, (5120, 13824, 40))])
+def test_batched_decode_skinny_gemm_equals_prefill_recompute(B, dims):
+    """BASELINE bs=32 decode at LLaVA-1.5-7B / 13B layer shapes (2 layers): every Linear of the step runs through the
+    swap-AB stream-K tcgen05 GEMM (csrc/gemm_skinny.cu: stream-K splits, SwiGLU epilogue, fp32 logits) replayed from a
+    CUDA graph; its logits must equal a prefill (tile GEMM + flash attention) over the extended sequence."""
+    h, I, H = dims
+    cfg = O.make_config(hidden=h, inter=I, layers=2, heads=H, vit_layers=2)
+    w = O.make_weights(cfg, seed=11)
+    eng = make_engine(cfg, w, max_batch=B, max_seq=160, max_images=1)
+    g = torch.Generator().manual_seed(5)
+    S_ = 100
+    embeds = (torch.randn(B, S_, h, generator=g) * 0.5).to(torch.bfloat16)
+    kv = eng.new_kv(B, 160)
+    last = eng.prefill(kv, embeds.to(DEV), None, _b2.LOGITS_LAST)
+    toks = last.argmax(-1).to(torch.int32)
+    ext = embeds
+    for step in range(3):  # step 0 runs eagerly, steps 1-2 replay the captured graph
+        lg = eng.decode_step(kv, toks)
+        ext = torch.cat([ext, w["model.embed_tokens.weight"][toks.cpu().long()][:, None].to(torch.bfloat16)], 1)
+        kv2 = eng.new_kv(B, 160)
+        ref = eng.prefill(kv2, ext.to(DEV), None, _b2.LOGITS_LAST)
+        _check(f"batched decode step {step} vs prefill recompute (B={B}, h={h})", lg, ref, tol_max=0.03, tol_mean=0.006)
+        kv2.close()
+        toks = lg.argmax(-1).to(torch.int32)
+    assert kv.lengths(B) == [S_ + 3] * B
+    kv.close()
+    eng.close()
+
+
 def test_decode_batch_above_8_uses_gemm_path_and_matches_oracle():
-    """B > 8 decode runs the skinny-M tcgen05 GEMM path (+ CUDA-graph replay); B <= 8 the persistent megakernel.
+    """B > 8 decode runs the swap-AB stream-K tcgen05 GEMM path (+ CUDA-graph replay); B <= 8 the GEMV kernels / the
+    persistent megakernel (B <= 2).
     Both must agree with the oracle and with each other on the shared samples."""
     cfg = O.CONFIGS["tiny"]
     w = O.make_weights(cfg, seed=0)

@@ -67,6 +67,9 @@ def assert_close(got, want, rtol=1.6e-2, atol=None):
     (1154, 4096, 1024, 256),    # BN=256 variant, 2 images
     (64, 32000, 4096, 128),     # decode-as-GEMM (B=64), fp32 logits shape
     (300, 136, 264, 64),        # everything ragged: M, N (not a tile multiple), K
+    (704, 4096, 4096, 192),     # BN=192: 132 tiles fill one wave of 148 SMs (last n-tile is 64 wide)
+    (577, 4096, 1024, 192),     # ViT fc1 at B=1
+    (300, 136, 264, 192),       # ragged everything through the 192-wide tile (N < BN)
 ])
 def test_gemm_plain(M, N, K, bn):
     A, W = rnd(M, K), rnd(N, K, scale=K ** -0.5)
@@ -79,6 +82,7 @@ def test_gemm_persistent_many_tiles():
     assert_close(gemm(A, W, bn=128), ref_linear(A, W))
     assert_close(gemm(A, W, bn=64), ref_linear(A, W))
     assert_close(gemm(A, W, bn=256), ref_linear(A, W))
+    assert_close(gemm(A, W, bn=192), ref_linear(A, W))
 
 
 @pytest.mark.parametrize("act", [_b2.ACT_NONE, _b2.ACT_QUICK_GELU, _b2.ACT_GELU_ERF])
