@@ -50,6 +50,12 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// MUFU.EX2 without exp2f's denormal-range fix-up (inputs here are <= 8, results feed a bf16 / an fp32 sum)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // smem descriptor for an MN-major bf16 operand tile stored as rows of 128 bytes (64 elements along MN) indexed by k,
@@ -208,24 +214,35 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             // one pass: the scaled, masked score row lives in registers (the d=64 variant runs 2 CTAs/SM under a 168-
             // register cap and spills part of it to L1-resident local memory; a second tcgen05.ld pass over S instead
             // was measured 30% slower: profiles/r1e_attn_tc_v2_twopass_2cta_SLOWER.txt)
-            float sc[TC_BN];
+            float sc[TC_BN];  // RAW scores (masked -> -inf); the softmax scale is folded into the exponent's FMA below
             float mx = -INFINITY;
+            // interior tiles need no per-key mask (CTA-uniform test: every key valid for every query row of this CTA)
+            const bool full_tile = (key0 + TC_BN <= len) && (!CAUSAL || key0 + TC_BN - 1 <= q0);
 #pragma unroll
             for (int c = 0; c < TC_BN / 32; ++c) {
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
                 tmem_ld_wait();
+                if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + c * 32 + i;
-                    bool ok = key < len;
-                    if (CAUSAL) ok = ok && (key <= qrow);
-                    const float x = ok ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-                    sc[c * 32 + i] = x;
-                    mx = fmaxf(mx, x);
+                    for (int i = 0; i < 32; ++i) {
+                        sc[c * 32 + i] = __uint_as_float(v[i]);
+                        mx = fmaxf(mx, sc[c * 32 + i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int key = key0 + c * 32 + i;
+                        bool ok = key < len;
+                        if (CAUSAL) ok = ok && (key <= qrow);
+                        const float x = ok ? __uint_as_float(v[i]) : -INFINITY;
+                        sc[c * 32 + i] = x;
+                        mx = fmaxf(mx, x);
+                    }
                 }
             }
+            mx *= p.scale_log2;  // scale > 0: max commutes with the scaling (-inf stays -inf)
             // lazy rescale: keep the stale max while the new one is < 2^8 above it (P <= 256: exact enough in bf16 / fp32;
             // the stale max cancels in O / l)
             const bool grow = mx > m_run + 8.0f;  // also true on the first valid tile (m_run = -inf)
@@ -258,7 +275,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 float pv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    pv[e] = exp2f(sc[ch * 8 + e] - m_use);
+                    pv[e] = ex2_approx(fmaf(sc[ch * 8 + e], p.scale_log2, -m_use));  // -inf -> +0
                     rs += pv[e];
                 }
                 const int sl = ch >> 3, cc = ch & 7;

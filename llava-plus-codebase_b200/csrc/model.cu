@@ -194,8 +194,10 @@ int skinny(b2_kv* kv, const void* x, int ldx, const void* W, int ldw, const void
     g.counters = kv->sk_counters.as<int>();
     return gemm_skinny_bf16(g, st);
 }
+// Batch 3..128 (the megakernel takes B <= 2). B2_DECODE_SKINNY=0 restores the round-1 paths for A/B runs: GEMV kernels
+// for B <= 8, the tile GEMM with the batch padded to a 128-row M tile above.
 bool use_skinny(const b2_kv* kv, int B) {
-    if (B <= 8 || B > 128 || kv->sk_partial.p == nullptr) return false;
+    if (B < 3 || B > 128 || kv->sk_partial.p == nullptr) return false;
     const char* e = getenv("B2_DECODE_SKINNY");
     return !(e != nullptr && e[0] == '0');
 }
@@ -367,9 +369,11 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const int nsplit = decode_nsplit(B, H);
     B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, st));
     // batch <= 8: tensor-core GEMV kernels (falls back to the skinny-M tcgen05 GEMM when the activations do not fit smem)
-    const bool small = B <= 8 && gemv_fits(B, h, I, ACT_NONE) && gemv_fits(B, 2 * I, h, ACT_SWIGLU) &&
+    // batch 3..128: swap-AB stream-K GEMM (weights streamed once, all SMs busy); otherwise GEMV kernels (B <= 8) or
+    // the tile GEMM
+    const bool sk = use_skinny(kv, B);
+    const bool small = !sk && B <= 8 && gemv_fits(B, h, I, ACT_NONE) && gemv_fits(B, 2 * I, h, ACT_SWIGLU) &&
                        gemv_fits(B, 3 * h, h, ACT_NONE) && gemv_fits(B, V, h, ACT_NONE);
-    const bool sk = !small && use_skinny(kv, B);  // batch 9..128: swap-AB stream-K GEMM (weights streamed once, all SMs)
     for (int l = 0; l < d.layers; ++l) {
         LlamaLayer& L = m->ll[l];
         if (small) {
@@ -547,7 +551,8 @@ int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     }
     B2_CUDA_CHECK(cudaGraphLaunch(kv->graph, st));
     // kernels per step: embed + L*(qkv, attn, o, gate/up, down [+2 norms when B>8]) + head(+norm) + argmax + 3
-    const bool small = B <= 8 && gemv_fits(B, m->d.hidden, m->d.inter, ACT_NONE) && gemv_fits(B, m->d.vocab, m->d.hidden, ACT_NONE);
+    const bool small = !use_skinny(kv, B) && B <= 8 && gemv_fits(B, m->d.hidden, m->d.inter, ACT_NONE) &&
+                       gemv_fits(B, m->d.vocab, m->d.hidden, ACT_NONE);
     const int per_layer = small ? 5 : 7;
     g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (small ? 1 : 2) + 4;
     return 0;
@@ -794,7 +799,7 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
         b2_kv_destroy(kv);
         return r;
     }
-    if (max_batch > 8 && max_batch <= 128) {
+    if (max_batch >= 3 && max_batch <= 128) {
         const int h = m->d.hidden, I = m->d.inter, V = m->d.vocab;
         size_t ws = 0;
         const int shapes[5][2] = {{3 * h, h}, {h, h}, {2 * I, h}, {h, I}, {V, h}};

@@ -311,6 +311,7 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         if max_new_tokens <= 0:
             raise ValueError("max_new_tokens must be positive")
         greedy = (not do_sample) or (temperature is not None and temperature <= 1e-5)
+        prof = _StageTimer() if os.environ.get("B2_PROFILE_GENERATE") else None
 
         # ---- prefill: splice + decoder, last-position logits only ----
         if images is not None and self.get_vision_tower() is not None:
@@ -326,9 +327,11 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             embeds = engine.splice(ids, None, B, Lt)
             lens = [Lt] * B
         S = embeds.shape[1]
+        if prof: prof.mark("encode_images+splice")
         kv = self._get_kv(B, max(lens) + max_new_tokens)
         kv.reset()
         logits = engine.prefill(kv, embeds, lens, LOGITS_LAST)
+        if prof: prof.mark("prefill")
 
         if streamer is not None:
             streamer.put(prompt.cpu())
@@ -338,10 +341,13 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             first = engine.argmax(logits)
             if max_new_tokens > 1:
                 rest = engine.decode_greedy(kv, first, max_new_tokens - 1)
+                if prof: prof.mark("decode_greedy")
                 new_tokens = torch.cat([first.unsqueeze(0), rest.to(first.device)], dim=0).t()
             else:
                 new_tokens = first.unsqueeze(1)
-            return torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
+            out = torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
+            if prof: prof.mark("ids to host"); prof.report()
+            return out
 
         out = prompt.clone()
         finished = torch.zeros(B, dtype=torch.bool)
@@ -405,6 +411,25 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
 
     def eval(self):
         return super().eval()
+
+
+class _StageTimer:
+    """B2_PROFILE_GENERATE=1: wall-clock per stage of generate() with a device sync at every mark (debug aid; the
+    syncs serialise host and device, so the stages add up to MORE than an unprofiled call)."""
+
+    def __init__(self):
+        import time
+        self._t, self._clock, self._rows = time.perf_counter(), time.perf_counter, []
+
+    def mark(self, name):
+        torch.cuda.synchronize()
+        t = self._clock()
+        self._rows.append((name, (t - self._t) * 1e3))
+        self._t = t
+
+    def report(self):
+        import sys
+        print("generate stages (ms): " + ", ".join(f"{n} {ms:.2f}" for n, ms in self._rows), file=sys.stderr)
 
 
 def _sample(logits, temperature, top_p, top_k):
