@@ -194,10 +194,15 @@ int skinny(b2_kv* kv, const void* x, int ldx, const void* W, int ldw, const void
     g.counters = kv->sk_counters.as<int>();
     return gemm_skinny_bf16(g, st);
 }
-// Batch 3..128 (the megakernel takes B <= 2). B2_DECODE_SKINNY=0 restores the round-1 paths for A/B runs: GEMV kernels
-// for B <= 8, the tile GEMM with the batch padded to a 128-row M tile above.
+// Batch 7..128. Measured ladder (7B, ms/step, profiles/r1e_config_sweep_*.jsonl): the stream-K GEMM path costs 4.13-4.19 for
+// every B <= 8 (7 kernels/layer, ~8 us of fixed cost per GEMM launch: profiles/r1e_decode_launch_shares_b4.txt), the GEMV
+// path (5 kernels/layer, RMSNorm fused) 3.63 at B=4 and 4.51 at B=8 -> crossover between 6 and 7. B2_DECODE_SKINNY=0
+// restores the round-1 paths for A/B runs (GEMV kernels for B <= 8, tile GEMM with the batch padded to M=128 above),
+// B2_DECODE_SKINNY=3 lowers the threshold to 3.
 bool use_skinny(const b2_kv* kv, int B) {
-    if (B < 3 || B > 128 || kv->sk_partial.p == nullptr) return false;
+    const char* e0 = getenv("B2_DECODE_SKINNY");
+    const int lo = (e0 != nullptr && e0[0] == '3') ? 3 : 7;
+    if (B < lo || B > 128 || kv->sk_partial.p == nullptr) return false;
     const char* e = getenv("B2_DECODE_SKINNY");
     return !(e != nullptr && e[0] == '0');
 }
@@ -369,7 +374,7 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const int nsplit = decode_nsplit(B, H);
     B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, st));
     // batch <= 8: tensor-core GEMV kernels (falls back to the skinny-M tcgen05 GEMM when the activations do not fit smem)
-    // batch 3..128: swap-AB stream-K GEMM (weights streamed once, all SMs busy); otherwise GEMV kernels (B <= 8) or
+    // batch 7..128: swap-AB stream-K GEMM (weights streamed once, all SMs busy); otherwise GEMV kernels (B <= 8) or
     // the tile GEMM
     const bool sk = use_skinny(kv, B);
     const bool small = !sk && B <= 8 && gemv_fits(B, h, I, ACT_NONE) && gemv_fits(B, 2 * I, h, ACT_SWIGLU) &&
