@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU")
     ap.add_argument("--prompt", type=int, default=128, help="text tokens (one <image> placeholder is added)")
     ap.add_argument("--new", type=int, default=256, help="greedy decode tokens")
+    ap.add_argument("--fp8", action="store_true",
+                    help="BASELINE configs[4]: e4m3 decoder weights/activations for decode at batch >= 7 (not yet GPU-validated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -63,10 +65,12 @@ def peaks():
         return 6650.0, 1590.0, "fallback"
 
 
-def algorithmic_work(m, B, S, N):
+def algorithmic_work(m, B, S, N, fp8=False):
     h, I, L = m["hidden"], m["inter"], m["layers"]
     layer_params = 4 * h * h + 3 * h * I
     w_bytes = 2 * (L * (layer_params + 2 * h) + h + VOCAB * h)     # decode weight stream (bf16), SURVEY §8d
+    if fp8:  # 1-byte Linear weights + one fp32 scale per output channel; norms stay bf16
+        w_bytes = L * (layer_params + 4 * (5 * h + 2 * I) + 2 * 2 * h) + 2 * h + VOCAB * (h + 4)
     kv_per_tok = 2 * 2 * h * L                                     # K+V bf16, all layers, per token per sample
     prefill_flops = B * (2 * S * layer_params * L + 2 * S * S * h * L + 2 * h * VOCAB)
     encode_flops = B * (VIT_GF * 1e9 + 2 * P_IMG * (1024 * h + h * h))
@@ -312,6 +316,10 @@ def run_ours(args):
     S = args.prompt + P_IMG
     model = build_model(m, dev, B, S + N + 8)
     engine = model._ensure_engine()
+    if args.fp8:
+        if B < 7:
+            raise ValueError("--fp8 only changes decode at batch >= 7 per GPU (smaller batches keep the bf16 paths)")
+        engine.enable_fp8_decode()
 
     g = torch.Generator().manual_seed(1 + rank)
     images_host = torch.randn(B, 3, 336, 336, generator=g).pin_memory()
@@ -321,7 +329,7 @@ def run_ours(args):
     ids_host = ids_host.pin_memory()
 
     stream = torch.cuda.Stream(device=dev)
-    work = algorithmic_work(m, B, S, N)
+    work = algorithmic_work(m, B, S, N, fp8=args.fp8)
     hbm_peak, tf_peak, peak_kind = peaks()
 
     with torch.cuda.stream(stream), torch.no_grad():
@@ -413,7 +421,9 @@ def run_ours(args):
     out = {
         "metric": "prefill+decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "e4m3 decoder Linears in decode (per-channel / per-token scales), bf16 elsewhere" if args.fp8 else "bf16",
+        "data": "synthetic",
         "config": workload_config(args, m, S),
         "breakdown": {"encode_images_ms": t_enc_m, "prefill_ms": t_pre_m, "decode_ms": t_dec_m,
                       "decode_ms_per_token": dec_step_ms, "images_per_s": world * B / (t_enc_m * 1e-3),

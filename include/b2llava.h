@@ -78,6 +78,12 @@ int b2_model_create(const b2_model_desc* desc, b2_model** out);
 int b2_model_set_weight(b2_model* m, const char* hf_key, const void* ptr, const int64_t* shape, int ndim, int dtype);
 int b2_model_finalize(b2_model* m);      /* checks every tensor arrived, allocates workspaces */
 int b2_model_destroy(b2_model* m);
+/* BASELINE configs[4] ("fp8-weight tcgen05 path"): after finalize, quantise the decoder's Linear weights to e4m3 with one
+ * fp32 scale per output channel; decode steps at batch >= 7 then run e4m3 x e4m3 tcgen05 GEMMs (activations quantised
+ * per token on the fly, KV cache stays bf16). Prefill and small-batch decode keep the bf16 weights. The reference has no
+ * fp8 path; oracle/fp8_oracle.py defines the arithmetic and the tolerance. NOT YET VALIDATED ON A GPU (drafted at the end
+ * of round 1 after the GPU budget was spent): off unless this call is made. */
+int b2_model_enable_fp8_decode(b2_model* m);
 
 int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out); /* KV cache [L][2][B][H][Smax][128] bf16 */
 int b2_kv_reset(b2_kv* kv);
@@ -131,6 +137,16 @@ int b2_op_gemv(const void* x, int64_t ldx, const void* W, int ldw, const void* n
 int b2_op_gemm_skinny(const void* x, int ldx, const void* W, int ldw, const void* residual, int ld_res, void* out,
                       int ld_out, int out_fp32, int B, int N, int K, int act, void* workspace, int64_t workspace_bytes,
                       void* counters, void* stream);
+/* fp8 variant of b2_op_gemm_skinny: xq [B,K] / Wq [N,K] e4m3 bytes (ld in bytes), x_scale [B], w_scale [N] fp32:
+ * out = (xq·Wq^T) * x_scale[b] * w_scale[n] (+ residual). Same scratch contract. */
+int b2_op_gemm_skinny_fp8(const void* xq, int ldx, const float* x_scale, const void* Wq, int ldw, const float* w_scale,
+                          const void* residual, int ld_res, void* out, int ld_out, int out_fp32, int B, int N, int K, int act,
+                          void* workspace, int64_t workspace_bytes, void* counters, void* stream);
+/* scale[r] = amax_r / 448 (1 for a zero row); q[r,k] = e4m3_rn_satfinite(x[r,k] * (448 / amax_r)); x bf16, ld in elements */
+int b2_op_quantize_rows_e4m3(const void* x, int64_t ldx, int rows, int K, void* q, int64_t ldq, float* scale, void* stream);
+/* LlamaRMSNorm (HF rounding points) fused with the per-token quantisation of its output; contiguous rows */
+int b2_op_rmsnorm_quant_e4m3(const void* x, const void* gamma, void* q, float* scale, int rows, int cols, float eps,
+                             void* stream);
 int64_t b2_op_gemm_skinny_workspace_bytes(int B, int N, int K);
 int64_t b2_op_gemm_skinny_counter_bytes(int N);
 int b2_op_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,

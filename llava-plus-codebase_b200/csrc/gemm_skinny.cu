@@ -14,6 +14,10 @@
 //     CTA to arrive, in fixed slot order (deterministic), which then runs the fused epilogue.
 //   * warp-specialised: 1 TMA producer thread (deep smem ring, ~200 KB in flight per SM), 1 MMA thread, 4 epilogue
 //     warps (tcgen05.ld -> transposed, coalesced stores: lane = weight row, consecutive lanes = consecutive n).
+//   * FP8 variant (template flag): e4m3 weights (per-output-channel fp32 scale) x e4m3 activations (per-token fp32 scale),
+//     tcgen05.mma kind::f8f6f4 (K = 32 per instruction, 128 elements per 128-byte swizzle row), dequantisation
+//     acc * w_scale[n] * x_scale[b] in the epilogue — BASELINE configs[4] ("fp8-weight tcgen05 path"): halves the weight
+//     stream. Same pipeline, same stream-K reduction. [drafted without GPU access at the end of round 1: not yet validated]
 // Replaces, for B > 8, the HF one-token Linear calls (transformers modeling_llama.py:251-289 q/k/v/o_proj, :182-184
 // LlamaMLP, :486-487 lm_head) behind the reference's decode branch (llava/model/llava_arch.py:103-112).
 #include <cuda.h>
@@ -25,11 +29,12 @@
 namespace b2 {
 
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int make_tmap_u8(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 namespace {
 
 constexpr int SK_BM = 128;          // weight rows per tile (UMMA M)
-constexpr int SK_BK = 64;           // 64 bf16 = one 128 B swizzle row
+constexpr int SK_BK = 64;           // bf16: 64 elements = one 128 B swizzle row (fp8: 128 elements, same bytes)
 constexpr int SK_THREADS = 192;     // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue (TMEM lane quadrant = warp % 4)
 constexpr int SK_W_TILE = SK_BM * SK_BK * 2;
 
@@ -49,7 +54,24 @@ struct SkEpi {
     float* partial;                 // stream-K workspace: [tile][maxseg][BN][128] fp32
     int* counters;                  // [tiles], zero-initialised, self-resetting
     int ld_out, ld_res, out_fp32, maxseg;
+    const float* w_scale;           // fp8 only: [N] per weight row (physical row order of W)
+    const float* x_scale;           // fp8 only: [B] per token
 };
+
+// kind::f8f6f4 instruction descriptor, A = B = e4m3 (format code 0), both K-major, D = fp32
+__host__ __device__ constexpr uint32_t make_idesc_e4m3_f32(uint32_t m, uint32_t n) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
@@ -61,7 +83,7 @@ __device__ __forceinline__ int sk_cta_of(long long u, long long total, int grid)
     return c;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, bool FP8>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, int N, int K,
                    int B, SkEpi ep) {
@@ -80,7 +102,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (N + SK_BM - 1) / SK_BM;
-    const int nkb = (K + SK_BK - 1) / SK_BK;
+    constexpr int BKE = FP8 ? 2 * SK_BK : SK_BK;  // elements per 128-byte k-block
+    const int nkb = (K + BKE - 1) / BKE;
     const long long total = (long long)num_m * nkb;
     const int grid = gridDim.x;
     const long long u0 = (total * blockIdx.x) / grid;
@@ -110,15 +133,15 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sw = smem + stage * Cfg::STAGE;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
-                    tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * SK_BK, t * SK_BM, kEvictFirst);
-                    tma_load_2d(sw + SK_W_TILE, &tmap_x, &full_bar[stage], kb * SK_BK, 0, kEvictLast);
+                    tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * BKE, t * SK_BM, kEvictFirst);
+                    tma_load_2d(sw + SK_W_TILE, &tmap_x, &full_bar[stage], kb * BKE, 0, kEvictLast);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc_bf16_f32(SK_BM, BN);
+            constexpr uint32_t idesc = FP8 ? make_idesc_e4m3_f32(SK_BM, BN) : make_idesc_bf16_f32(SK_BM, BN);
             int stage = 0; uint32_t phase = 0; int local = 0;
             for (int t = t_first; t <= t_last; ++t, ++local) {
                 const int kb0 = (int)(max(u0, (long long)t * nkb) - (long long)t * nkb);
@@ -134,8 +157,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     const uint64_t da = make_sw128_kmajor_desc(sw);
                     const uint64_t db = make_sw128_kmajor_desc(sw + SK_W_TILE);
 #pragma unroll
-                    for (int k = 0; k < SK_BK / 16; ++k)
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {  // 32 bytes of K per instruction: 16 bf16 / 32 e4m3
+                        if constexpr (FP8) umma_f8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -197,6 +222,15 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                         for (int j = 0; j < 32; ++j) acc[j] += __ldcg(ps + (size_t)j * SK_BM);
                     }
                 }
+                if constexpr (FP8) {  // dequantise: per weight row (this thread's TMEM lane) x per token (column)
+                    const int nrow = t * SK_BM + row_in_tile;
+                    const float ws = (finalize && nrow < N) ? __ldg(ep.w_scale + nrow) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int b = c * 32 + j;
+                        acc[j] *= ws * (b < B ? __ldg(ep.x_scale + b) : 0.f);
+                    }
+                }
                 if constexpr (ACT == ACT_SWIGLU) {
                     // tile rows [0,64) = gate, [64,128) = up of channels t*64 + (0..63): up rows go through smem
                     if (finalize && q >= 2) {
@@ -249,11 +283,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
 struct SkPlan { int bn, num_m, nkb, grid, maxseg; long long total; };
 
-SkPlan sk_plan(int B, int N, int K) {
+SkPlan sk_plan(int B, int N, int K, bool fp8 = false) {
     SkPlan p;
+    const int bke = fp8 ? 2 * SK_BK : SK_BK;
     p.bn = B <= 32 ? 32 : (B <= 64 ? 64 : 128);
     p.num_m = (N + SK_BM - 1) / SK_BM;
-    p.nkb = (K + SK_BK - 1) / SK_BK;
+    p.nkb = (K + bke - 1) / bke;
     p.total = (long long)p.num_m * p.nkb;
     p.grid = (long long)num_sms() < p.total ? num_sms() : (int)p.total;
     const long long per_min = p.total / p.grid;  // >= 1
@@ -261,12 +296,12 @@ SkPlan sk_plan(int B, int N, int K) {
     return p;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, bool FP8>
 int sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkPlan& pl, int N, int K, int B, const SkEpi& ep,
               cudaStream_t st) {
     using Cfg = SkCfg<BN>;
     static bool attr_set = false;
-    auto kern = gemm_skinny_kernel<BN, ACT>;
+    auto kern = gemm_skinny_kernel<BN, ACT, FP8>;
     if (!attr_set) {
         B2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set = true;
@@ -278,38 +313,52 @@ int sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkPlan& pl, in
 
 }  // namespace
 
+// scratch that satisfies BOTH element types (the fp8 plan has half the k-blocks per tile and can need one slot more)
 size_t gemm_skinny_workspace_bytes(int B, int N, int K) {
-    const SkPlan p = sk_plan(B, N, K);
-    return (size_t)p.num_m * p.maxseg * p.bn * SK_BM * sizeof(float);
+    const SkPlan p = sk_plan(B, N, K, false), q = sk_plan(B, N, K, true);
+    const int maxseg = p.maxseg > q.maxseg ? p.maxseg : q.maxseg;
+    return (size_t)p.num_m * maxseg * p.bn * SK_BM * sizeof(float);
 }
 size_t gemm_skinny_counter_bytes(int N) { return (size_t)((N + SK_BM - 1) / SK_BM) * sizeof(int); }
 
-int gemm_skinny_bf16(const SkinnyArgs& g, cudaStream_t stream) {
+template <bool FP8>
+static int gemm_skinny_any(const SkinnyArgs& g, cudaStream_t stream) {
     B2_CHECK_ARG(g.B >= 1 && g.B <= 128 && g.N > 0 && g.K > 0, "gemm_skinny: bad problem B=%d N=%d K=%d", g.B, g.N, g.K);
-    B2_CHECK_ARG(g.K % 8 == 0, "gemm_skinny: K must be a multiple of 8 (K=%d)", g.K);
+    B2_CHECK_ARG(g.K % (FP8 ? 16 : 8) == 0, "gemm_skinny: K must be a multiple of %d (K=%d)", FP8 ? 16 : 8, g.K);
     B2_CHECK_ARG(g.act == ACT_NONE || g.act == ACT_SWIGLU, "gemm_skinny: unsupported activation %d", g.act);
     B2_CHECK_ARG(g.act != ACT_SWIGLU || (g.N % 128 == 0 && !g.out_fp32 && g.residual == nullptr),
                  "gemm_skinny: swiglu needs N %% 128 == 0, bf16 output, no residual (N=%d)", g.N);
     B2_CHECK_ARG(g.partial != nullptr && g.counters != nullptr, "gemm_skinny: workspace missing");
-    const SkPlan pl = sk_plan(g.B, g.N, g.K);
-    B2_CHECK_ARG(g.partial_bytes >= gemm_skinny_workspace_bytes(g.B, g.N, g.K),
-                 "gemm_skinny: workspace too small (%zu < %zu)", g.partial_bytes, gemm_skinny_workspace_bytes(g.B, g.N, g.K));
+    B2_CHECK_ARG(!FP8 || (g.w_scale != nullptr && g.x_scale != nullptr), "gemm_skinny(fp8): scale vectors missing");
+    const SkPlan pl = sk_plan(g.B, g.N, g.K, FP8);
+    B2_CHECK_ARG(g.partial_bytes >= (size_t)pl.num_m * pl.maxseg * pl.bn * SK_BM * sizeof(float),
+                 "gemm_skinny: workspace too small (%zu bytes)", g.partial_bytes);
     CUtensorMap tw, tx;
-    B2_TRY(make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, SK_BM));
-    B2_TRY(make_tmap_bf16(&tx, g.x, g.B, g.K, g.ldx, pl.bn));
+    if (FP8) {
+        B2_TRY(make_tmap_u8(&tw, g.W, g.N, g.K, g.ldw, SK_BM));
+        B2_TRY(make_tmap_u8(&tx, g.x, g.B, g.K, g.ldx, pl.bn));
+    } else {
+        B2_TRY(make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, SK_BM));
+        B2_TRY(make_tmap_bf16(&tx, g.x, g.B, g.K, g.ldx, pl.bn));
+    }
     SkEpi ep;
     ep.residual = reinterpret_cast<const __nv_bfloat16*>(g.residual);
     ep.out = g.out; ep.partial = g.partial; ep.counters = g.counters;
     ep.ld_out = g.ld_out; ep.ld_res = g.ld_res; ep.out_fp32 = g.out_fp32; ep.maxseg = pl.maxseg;
+    ep.w_scale = g.w_scale; ep.x_scale = g.x_scale;
     const bool sw = g.act == ACT_SWIGLU;
     switch (pl.bn) {
-        case 32: return sw ? sk_launch<32, ACT_SWIGLU>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
-                           : sk_launch<32, ACT_NONE>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
-        case 64: return sw ? sk_launch<64, ACT_SWIGLU>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
-                           : sk_launch<64, ACT_NONE>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
-        default: return sw ? sk_launch<128, ACT_SWIGLU>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
-                           : sk_launch<128, ACT_NONE>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
+        case 32: return sw ? sk_launch<32, ACT_SWIGLU, FP8>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
+                           : sk_launch<32, ACT_NONE, FP8>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
+        case 64: return sw ? sk_launch<64, ACT_SWIGLU, FP8>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
+                           : sk_launch<64, ACT_NONE, FP8>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
+        default: return sw ? sk_launch<128, ACT_SWIGLU, FP8>(tw, tx, pl, g.N, g.K, g.B, ep, stream)
+                           : sk_launch<128, ACT_NONE, FP8>(tw, tx, pl, g.N, g.K, g.B, ep, stream);
     }
 }
+
+int gemm_skinny_bf16(const SkinnyArgs& g, cudaStream_t stream) { return gemm_skinny_any<false>(g, stream); }
+// x and W hold e4m3 bytes (ldx / ldw in elements = bytes); w_scale [N], x_scale [B] fp32
+int gemm_skinny_fp8(const SkinnyArgs& g, cudaStream_t stream) { return gemm_skinny_any<true>(g, stream); }
 
 }  // namespace b2

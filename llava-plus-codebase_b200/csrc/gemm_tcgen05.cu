@@ -72,6 +72,32 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols
     return 0;
 }
 
+// 2D byte tensor (fp8 operands) row-major [rows, cols] with row pitch ld bytes; box = [box_rows, 128 B]. gemm_skinny.cu.
+int make_tmap_u8(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return -2;
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ld % 16 != 0) {
+        set_error("TMA operand must be 16B aligned with a 16B-multiple row pitch (ptr=%p ld=%lld)", ptr, (long long)ld);
+        return -1;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld};
+    cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(u8) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld);
+        return -2;
+    }
+    return 0;
+}
+
 namespace {
 
 constexpr int BM = 128;

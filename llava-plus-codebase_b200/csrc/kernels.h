@@ -38,10 +38,20 @@ struct SkinnyArgs {
     int act = ACT_NONE;                          // ACT_NONE | ACT_SWIGLU
     float* partial = nullptr; size_t partial_bytes = 0;  // >= gemm_skinny_workspace_bytes(B, N, K)
     int* counters = nullptr;                     // >= gemm_skinny_counter_bytes(N), zero-initialised once
+    const float* w_scale = nullptr;              // fp8 variant: [N] per weight row; x / W then hold e4m3 bytes
+    const float* x_scale = nullptr;              // fp8 variant: [B] per token
 };
 int gemm_skinny_bf16(const SkinnyArgs& g, cudaStream_t stream);
+int gemm_skinny_fp8(const SkinnyArgs& g, cudaStream_t stream);   // [unvalidated draft, see gemm_skinny.cu]
 size_t gemm_skinny_workspace_bytes(int B, int N, int K);
 size_t gemm_skinny_counter_bytes(int N);
+
+// ---- e4m3 row quantisation for the fp8 decode path (quant_fp8.cu) [unvalidated draft] ----------------------
+// scale[r] = amax_r / 448 (1 for a zero row); q[r,k] = e4m3_rn_satfinite(x[r,k] * (448 / amax_r)); ld* in elements
+int quantize_rows_e4m3(const void* x, int64_t ldx, int rows, int K, void* q, int64_t ldq, float* scale, cudaStream_t stream);
+// RMSNorm (HF rounding points) fused with the per-token quantisation of its output
+int rmsnorm_quant_e4m3(const void* x, int64_t x_row_stride, const void* gamma, void* q, int64_t ldq, float* scale, int rows,
+                       int cols, float eps, cudaStream_t stream);
 
 // ---- weight-streaming GEMV for decode (gemv.cu) ---------------------------------------------------
 // out[B, N] = (rmsnorm(x) or x)[B,K] · W[N,K]^T (+ residual); B <= 8. ACT_SWIGLU: out[B, N/2].

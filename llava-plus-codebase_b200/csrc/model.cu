@@ -60,6 +60,7 @@ struct VitLayer {
 };
 struct LlamaLayer {
     DevBuf ln1, wqkv, wo, ln2, wgu, wd;
+    DevBuf wqkv8, wo8, wgu8, wd8, s_qkv, s_o, s_gu, s_d;  // e4m3 copies + per-row fp32 scales (b2_model_enable_fp8_decode)
     DevBuf tmp_gate, tmp_up;  // staging until both halves arrived
     bool has_gate = false, has_up = false;
 };
@@ -86,6 +87,9 @@ struct b2_model {
     DevBuf v_col, v_patch, v_hidden, v_xn, v_qkv, v_attn, v_mlp, v_feats, p_mid;
     // LLaMA workspace
     DevBuf x, xn, qkv, attn, act, last_idx, xlast, logits;
+    // fp8 decode (BASELINE configs[4]): e4m3 lm_head + scales, quantised activation row buffer + per-token scales
+    bool fp8_decode = false;
+    DevBuf lm_head8, s_head, xq8, xscale;
 };
 
 struct b2_kv {
@@ -199,6 +203,17 @@ int skinny(b2_kv* kv, const void* x, int ldx, const void* W, int ldw, const void
 // path (5 kernels/layer, RMSNorm fused) 3.63 at B=4 and 4.51 at B=8 -> crossover between 6 and 7. B2_DECODE_SKINNY=0
 // restores the round-1 paths for A/B runs (GEMV kernels for B <= 8, tile GEMM with the batch padded to M=128 above),
 // B2_DECODE_SKINNY=3 lowers the threshold to 3.
+// fp8 variant: xq8 / xscale hold the quantised activations of this GEMM
+int skinny8(b2_model* m, b2_kv* kv, const void* W8, const float* w_scale, const void* res, int ld_res, void* out, int ld_out,
+            int out_fp32, int B, int N, int K, int act, cudaStream_t st) {
+    SkinnyArgs g;
+    g.x = m->xq8.p; g.ldx = K; g.W = W8; g.ldw = K; g.residual = res; g.ld_res = ld_res;
+    g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.B = B; g.N = N; g.K = K; g.act = act;
+    g.partial = kv->sk_partial.as<float>(); g.partial_bytes = kv->sk_partial.bytes;
+    g.counters = kv->sk_counters.as<int>();
+    g.w_scale = w_scale; g.x_scale = m->xscale.as<float>();
+    return gemm_skinny_fp8(g, st);
+}
 bool use_skinny(const b2_kv* kv, int B) {
     const char* e0 = getenv("B2_DECODE_SKINNY");
     const int lo = (e0 != nullptr && e0[0] == '3') ? 3 : 7;
@@ -379,9 +394,13 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const bool sk = use_skinny(kv, B);
     const bool small = !sk && B <= 8 && gemv_fits(B, h, I, ACT_NONE) && gemv_fits(B, 2 * I, h, ACT_SWIGLU) &&
                        gemv_fits(B, 3 * h, h, ACT_NONE) && gemv_fits(B, V, h, ACT_NONE);
+    const bool f8 = sk && m->fp8_decode;  // e4m3 weights x e4m3 activations through the same stream-K GEMM
     for (int l = 0; l < d.layers; ++l) {
         LlamaLayer& L = m->ll[l];
-        if (small) {
+        if (f8) {
+            B2_TRY(rmsnorm_quant_e4m3(m->x.p, h, L.ln1.p, m->xq8.p, h, m->xscale.as<float>(), B, h, d.rms_eps, st));
+            B2_TRY(skinny8(m, kv, L.wqkv8.p, L.s_qkv.as<float>(), nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h, ACT_NONE, st));
+        } else if (small) {
             B2_TRY(gemv(m->x.p, h, L.wqkv.p, h, L.ln1.p, d.rms_eps, nullptr, 0, m->qkv.p, 3 * h, 0, B, 3 * h, h,
                         ACT_NONE, st));
         } else if (sk) {
@@ -403,7 +422,14 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
         da.theta = d.rope_theta;
         da.scale = 1.0f / sqrtf((float)m->hd);
         B2_TRY(decode_attn_bf16(da, st));
-        if (small) {
+        if (f8) {
+            B2_TRY(quantize_rows_e4m3(m->attn.p, h, B, h, m->xq8.p, h, m->xscale.as<float>(), st));
+            B2_TRY(skinny8(m, kv, L.wo8.p, L.s_o.as<float>(), m->x.p, h, m->x.p, h, 0, B, h, h, ACT_NONE, st));
+            B2_TRY(rmsnorm_quant_e4m3(m->x.p, h, L.ln2.p, m->xq8.p, h, m->xscale.as<float>(), B, h, d.rms_eps, st));
+            B2_TRY(skinny8(m, kv, L.wgu8.p, L.s_gu.as<float>(), nullptr, 0, m->act.p, I, 0, B, 2 * I, h, ACT_SWIGLU, st));
+            B2_TRY(quantize_rows_e4m3(m->act.p, I, B, I, m->xq8.p, I, m->xscale.as<float>(), st));
+            B2_TRY(skinny8(m, kv, L.wd8.p, L.s_d.as<float>(), m->x.p, h, m->x.p, h, 0, B, h, I, ACT_NONE, st));
+        } else if (small) {
             B2_TRY(gemv(m->attn.p, h, L.wo.p, h, nullptr, 0.f, m->x.p, h, m->x.p, h, 0, B, h, h, ACT_NONE, st));
             B2_TRY(gemv(m->x.p, h, L.wgu.p, h, L.ln2.p, d.rms_eps, nullptr, 0, m->act.p, I, 0, B, 2 * I, h,
                         ACT_SWIGLU, st));
@@ -420,7 +446,10 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
             B2_TRY(gemm(m->act.p, I, L.wd.p, I, nullptr, m->x.p, h, m->x.p, h, 0, B, h, I, ACT_NONE, st));
         }
     }
-    if (small) {
+    if (f8) {
+        B2_TRY(rmsnorm_quant_e4m3(m->x.p, h, m->final_norm.p, m->xq8.p, h, m->xscale.as<float>(), B, h, d.rms_eps, st));
+        B2_TRY(skinny8(m, kv, m->lm_head8.p, m->s_head.as<float>(), nullptr, 0, m->logits.p, V, 1, B, V, h, ACT_NONE, st));
+    } else if (small) {
         B2_TRY(gemv(m->x.p, h, m->lm_head.p, h, m->final_norm.p, d.rms_eps, nullptr, 0, m->logits.p, V, 1, B, V, h,
                     ACT_NONE, st));
     } else if (sk) {
@@ -558,7 +587,7 @@ int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     // kernels per step: embed + L*(qkv, attn, o, gate/up, down [+2 norms when B>8]) + head(+norm) + argmax + 3
     const bool small = !use_skinny(kv, B) && B <= 8 && gemv_fits(B, m->d.hidden, m->d.inter, ACT_NONE) &&
                        gemv_fits(B, m->d.vocab, m->d.hidden, ACT_NONE);
-    const int per_layer = small ? 5 : 7;
+    const int per_layer = small ? 5 : ((m->fp8_decode && use_skinny(kv, B)) ? 9 : 7);
     g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (small ? 1 : 2) + 4;
     return 0;
 }
@@ -747,17 +776,49 @@ int b2_model_destroy(b2_model* m) {
     DevBuf* top[] = {&m->patch_w, &m->cls, &m->pos, &m->pre_g, &m->pre_b, &m->p0_w, &m->p0_b, &m->p2_w, &m->p2_b,
                      &m->embed, &m->final_norm, &m->lm_head, &m->v_col, &m->v_patch, &m->v_hidden, &m->v_xn,
                      &m->v_qkv, &m->v_attn, &m->v_mlp, &m->v_feats, &m->p_mid, &m->x, &m->xn, &m->qkv, &m->attn,
-                     &m->act, &m->last_idx, &m->xlast, &m->logits};
+                     &m->act, &m->last_idx, &m->xlast, &m->logits, &m->lm_head8, &m->s_head, &m->xq8, &m->xscale};
     for (DevBuf* b : top) b->free();
     for (VitLayer& L : m->vit) {
         DevBuf* bs[12] = {&L.ln1_g, &L.ln1_b, &L.wqkv, &L.bqkv, &L.wo, &L.bo, &L.ln2_g, &L.ln2_b, &L.w1, &L.b1, &L.w2, &L.b2};
         for (DevBuf* b : bs) b->free();
     }
     for (LlamaLayer& L : m->ll) {
-        DevBuf* bs[8] = {&L.ln1, &L.wqkv, &L.wo, &L.ln2, &L.wgu, &L.wd, &L.tmp_gate, &L.tmp_up};
+        DevBuf* bs[16] = {&L.ln1, &L.wqkv, &L.wo, &L.ln2, &L.wgu, &L.wd, &L.tmp_gate, &L.tmp_up,
+                          &L.wqkv8, &L.wo8, &L.wgu8, &L.wd8, &L.s_qkv, &L.s_o, &L.s_gu, &L.s_d};
         for (DevBuf* b : bs) b->free();
     }
     delete m;
+    return 0;
+}
+
+// BASELINE configs[4]: quantise every decode Linear to e4m3 with per-output-channel scales (the bf16 copies stay: prefill
+// and the B <= 6 decode paths keep using them). Decode steps at batch >= 7 then stream 1-byte weights.
+int b2_model_enable_fp8_decode(b2_model* m) {
+    B2_CHECK_ARG(m != nullptr, "b2_model_enable_fp8_decode: null model");
+    B2_CHECK_ARG(m->finalized, "b2_model_enable_fp8_decode: model not finalized");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    if (m->fp8_decode) return 0;
+    const b2_model_desc& d = m->d;
+    const int h = d.hidden, I = d.inter, V = d.vocab;
+    B2_CHECK_ARG(h % 16 == 0 && I % 16 == 0, "b2_model_enable_fp8_decode: hidden/inter must be multiples of 16");
+    auto quant = [&](DevBuf& w, int N, int K, DevBuf& w8, DevBuf& sc) -> int {
+        B2_TRY(w8.alloc((size_t)N * K));
+        B2_TRY(sc.alloc((size_t)N * sizeof(float)));
+        return quantize_rows_e4m3(w.p, K, N, K, w8.p, K, sc.as<float>(), nullptr);
+    };
+    for (LlamaLayer& L : m->ll) {
+        B2_TRY(quant(L.wqkv, 3 * h, h, L.wqkv8, L.s_qkv));
+        B2_TRY(quant(L.wo, h, h, L.wo8, L.s_o));
+        B2_TRY(quant(L.wgu, 2 * I, h, L.wgu8, L.s_gu));  // rows stay block-64 interleaved; scales follow the physical rows
+        B2_TRY(quant(L.wd, h, I, L.wd8, L.s_d));
+    }
+    B2_TRY(quant(m->lm_head, V, h, m->lm_head8, m->s_head));
+    const int mb = d.max_batch > 128 ? 128 : d.max_batch;
+    B2_TRY(m->xq8.alloc((size_t)mb * (h > I ? h : I)));
+    B2_TRY(m->xscale.alloc((size_t)mb * sizeof(float)));
+    B2_CUDA_CHECK(cudaDeviceSynchronize());
+    m->fp8_decode = true;
     return 0;
 }
 
@@ -1069,6 +1130,27 @@ int b2_op_gemm_skinny(const void* x, int ldx, const void* W, int ldw, const void
     g.partial = reinterpret_cast<float*>(workspace); g.partial_bytes = (size_t)workspace_bytes;
     g.counters = reinterpret_cast<int*>(counters);
     return gemm_skinny_bf16(g, reinterpret_cast<cudaStream_t>(stream));
+}
+int b2_op_gemm_skinny_fp8(const void* xq, int ldx, const float* x_scale, const void* Wq, int ldw, const float* w_scale,
+                          const void* residual, int ld_res, void* out, int ld_out, int out_fp32, int B, int N, int K, int act,
+                          void* workspace, int64_t workspace_bytes, void* counters, void* stream) {
+    B2_CHECK_ARG(xq && Wq && x_scale && w_scale && out && workspace && counters, "b2_op_gemm_skinny_fp8: null argument");
+    SkinnyArgs g;
+    g.x = xq; g.ldx = ldx; g.W = Wq; g.ldw = ldw; g.residual = residual; g.ld_res = ld_res;
+    g.out = out; g.ld_out = ld_out; g.out_fp32 = out_fp32; g.B = B; g.N = N; g.K = K; g.act = act;
+    g.partial = reinterpret_cast<float*>(workspace); g.partial_bytes = (size_t)workspace_bytes;
+    g.counters = reinterpret_cast<int*>(counters);
+    g.w_scale = w_scale; g.x_scale = x_scale;
+    return gemm_skinny_fp8(g, reinterpret_cast<cudaStream_t>(stream));
+}
+int b2_op_quantize_rows_e4m3(const void* x, int64_t ldx, int rows, int K, void* q, int64_t ldq, float* scale, void* stream) {
+    B2_CHECK_ARG(x && q && scale, "b2_op_quantize_rows_e4m3: null argument");
+    return quantize_rows_e4m3(x, ldx, rows, K, q, ldq, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+int b2_op_rmsnorm_quant_e4m3(const void* x, const void* gamma, void* q, float* scale, int rows, int cols, float eps,
+                             void* stream) {
+    B2_CHECK_ARG(x && gamma && q && scale, "b2_op_rmsnorm_quant_e4m3: null argument");
+    return rmsnorm_quant_e4m3(x, cols, gamma, q, cols, scale, rows, cols, eps, reinterpret_cast<cudaStream_t>(stream));
 }
 int64_t b2_op_gemm_skinny_workspace_bytes(int B, int N, int K) {
     if (B < 1 || B > 128 || N < 1 || K < 1) return -1;

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b2_model_set_weight": (_i32, [_vp, _c.c_char_p, _vp, _c.POINTER(_i64), _i32, _i32]),
     "b2_model_finalize": (_i32, [_vp]),
     "b2_model_destroy": (_i32, [_vp]),
+    "b2_model_enable_fp8_decode": (_i32, [_vp]),
     "b2_kv_create": (_i32, [_vp, _i32, _i32, _c.POINTER(_vp)]),
     "b2_kv_reset": (_i32, [_vp]),
     "b2_kv_destroy": (_i32, [_vp]),
@@ -61,6 +62,9 @@ SIGNATURES = {
     "b2_op_gemm": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b2_op_gemv": (_i32, [_vp, _i64, _vp, _i32, _vp, _f32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b2_op_gemm_skinny": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "b2_op_gemm_skinny_fp8": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "b2_op_quantize_rows_e4m3": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "b2_op_rmsnorm_quant_e4m3": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "b2_op_gemm_skinny_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "b2_op_gemm_skinny_counter_bytes": (_i64, [_i32]),
     "b2_op_layernorm": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
@@ -208,6 +212,11 @@ class Engine:
         with torch.cuda.device(self.index):
             check(self.lib.b2_model_finalize(self.handle), "b2_model_finalize")
         self.finalized = True
+
+    def enable_fp8_decode(self):
+        """BASELINE configs[4]: e4m3 weights for decode at batch >= 7 (see include/b2llava.h; unvalidated draft)."""
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_model_enable_fp8_decode(self.handle), "b2_model_enable_fp8_decode")
 
     def new_kv(self, max_batch, max_seq):
         with torch.cuda.device(self.index):

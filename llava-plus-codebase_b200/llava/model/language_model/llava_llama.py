@@ -193,6 +193,9 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
                 continue
             eng.set_weight(k, v.to(self.device))
         eng.finalize()
+        # BASELINE configs[4] opt-in: e4m3 decoder weights for batch >= 7 decode (config.b2_fp8_decode or B2_FP8_DECODE=1)
+        if getattr(c, "b2_fp8_decode", False) or os.environ.get("B2_FP8_DECODE") == "1":
+            eng.enable_fp8_decode()
         self._engine = eng
         self._kv = None
         return eng

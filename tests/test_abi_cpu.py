@@ -56,3 +56,23 @@ def test_product_never_imports_oracle(repo_root):
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), f"{f} references the oracle"
+
+
+def test_stream_k_plan_helpers_are_host_only():
+    """The stream-K GEMM's scratch sizing is pure host arithmetic (no GPU needed): the workspace holds, per 128-row
+    weight tile, one [BN x 128] fp32 slot for every CTA that can share the tile; BN is the batch rounded up to 32/64/128."""
+    from llava import _b2
+
+    lib = _b2.load_library()
+    slot = lambda bn: bn * 128 * 4
+    for B, N, K in [(7, 4096, 4096), (32, 12288, 4096), (33, 4096, 11008), (128, 32000, 4096), (20, 200, 264)]:
+        ws = lib.b2_op_gemm_skinny_workspace_bytes(B, N, K)
+        bn = 32 if B <= 32 else (64 if B <= 64 else 128)
+        tiles = (N + 127) // 128
+        assert ws > 0 and ws % (tiles * slot(bn)) == 0, (B, N, K, ws)
+        segs = ws // (tiles * slot(bn))
+        assert 2 <= segs <= (K + 63) // 64 + 1  # at least own slot + one neighbour, never more than the k-blocks of a tile
+        assert lib.b2_op_gemm_skinny_counter_bytes(N) == tiles * 4
+    assert lib.b2_op_gemm_skinny_workspace_bytes(0, 128, 64) == -1
+    assert lib.b2_op_gemm_skinny_workspace_bytes(129, 128, 64) == -1
+    assert lib.b2_op_gemm_skinny_counter_bytes(0) == -1
