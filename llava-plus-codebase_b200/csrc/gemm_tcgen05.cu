@@ -11,6 +11,7 @@
 //     LlamaMLP, :303-332 residual adds; llava/model/multimodal_projector/builder.py:42-46).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -405,6 +406,13 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     B2_CHECK_ARG(g.residual == nullptr ||
                      ((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ld_res % 8) == 0),
                  "gemm: residual must be 16B aligned with ld_res %% 8 == 0");
+
+    // CTA-pair kernel (draft, never run on a GPU yet): only on request
+    if (g.bn_override == 2) return gemm_bf16_2cta(g, stream);
+    if (g.bn_override == 0 && g.M >= 1024 && g.N >= 512) {
+        const char* e = getenv("B2_GEMM_2CTA");
+        if (e != nullptr && e[0] == '1') return gemm_bf16_2cta(g, stream);
+    }
 
     // Tile-N choice. Cost model fitted to profiles/r1b_gemm_sweep.json: a tile costs ~BN / rel(BN) (rel = tensor-pipe
     // feed efficiency of the shape: BN=256 needs 96 B/clk of smem operand traffic, BN=128 sits on the 128 B/clk limit,

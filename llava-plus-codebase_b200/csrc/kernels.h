@@ -23,9 +23,11 @@ struct GemmArgs {
     void* out = nullptr; int ld_out = 0; int out_fp32 = 0;
     int M = 0, N = 0, K = 0;
     int act = ACT_NONE;
-    int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256
+    int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256 (2 = CTA-pair kernel, draft)
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+// CTA-pair (cta_group::2, 256x256 pair tiles) variant, gemm_2cta.cu [unvalidated draft: B2_GEMM_2CTA=1 or bn_override == 2]
+int gemm_bf16_2cta(const GemmArgs& g, cudaStream_t stream);
 
 // ---- swap-AB stream-K GEMM for decode at batch 9..128 (gemm_skinny.cu) ------------------------------------
 // out[B, N] = x[B,K] · W[N,K]^T (+ residual); ACT_SWIGLU: out[B, N/2] (W rows block-64 interleaved).

@@ -133,6 +133,32 @@ def test_gemm_linearity_and_determinism():
     assert torch.equal(gemm(A1, W, out_fp32=True), c1)
 
 
+# ------------------------------------------------------------------------- CTA-pair (cta_group::2) GEMM — draft
+_pair = pytest.mark.skipif(__import__("os").environ.get("B2_TEST_2CTA") != "1",
+                           reason="gemm_2cta.cu was written without GPU access (end of round 1): run with B2_TEST_2CTA=1")
+
+
+@_pair
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 512), (704, 4096, 4096), (9232, 3072, 1024),
+                                   (9232, 1024, 4096), (5632, 12288, 4096), (300, 136, 264)])
+def test_gemm_2cta_plain(M, N, K):
+    A, W = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    assert_close(gemm(A, W, bn=2), ref_linear(A, W))
+
+
+@_pair
+def test_gemm_2cta_epilogues_match_the_1cta_kernel():
+    M, N, K = 1154, 4096, 1024
+    A, W, b, r = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(N), rnd(M, N)
+    for act in (_b2.ACT_NONE, _b2.ACT_QUICK_GELU, _b2.ACT_GELU_ERF):  # same operands, same fp32 accumulation: <= 1 bf16 ulp apart
+        assert_close(gemm(A, W, bias=b, residual=r, act=act, bn=2), gemm(A, W, bias=b, residual=r, act=act, bn=256), rtol=8e-3)
+    torch.testing.assert_close(gemm(A, W, out_fp32=True, bn=2), gemm(A, W, out_fp32=True, bn=256), rtol=1e-4, atol=1e-4)
+    x, Wg, Wu = rnd(704, 4096), rnd(11008, 4096, scale=1 / 64), rnd(11008, 4096, scale=1 / 64)
+    Wgu = torch.empty(2 * 11008, 4096, device=DEV, dtype=BF)
+    _b2.check(_b2.load_library().b2_op_interleave_gate_up(P(Wg), P(Wu), P(Wgu), 11008, 4096, S()))
+    assert_close(gemm(x, Wgu, act=_b2.ACT_SWIGLU, bn=2), gemm(x, Wgu, act=_b2.ACT_SWIGLU, bn=256), rtol=8e-3)
+
+
 # ------------------------------------------------------------------------- skinny (swap-AB stream-K) GEMM
 def skinny(x, W, residual=None, act=_b2.ACT_NONE, out_fp32=False, out=None, scratch=None):
     B, K = x.shape
