@@ -297,6 +297,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
     }
 
+    __syncwarp();  // lanes 1..31 of the producer / MMA warps waited here: the cluster barrier below is .aligned
     tc_fence_before();
     cluster_sync_all();  // no CTA may free TMEM / exit while its partner can still signal into its shared memory
     if (warp == 1) {
