@@ -3,8 +3,8 @@
 # of the dominant kernels. Numbers printed under ncu are never bench values.
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD:$PWD/llava-plus-codebase_b200:$PYTHONPATH
-echo "=== ncu launch list (bench command, 1 timed step; -k keeps the weight-init kernels of the synthetic model out)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"b2::|elementwise" --csv --log-file gpurun_out/launches.csv \
+echo "=== ncu launch list (bench command, 1 timed step; -k takes BASE kernel names and keeps the weight-init kernels of the synthetic model out)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"decode_mega|gemm_bf16_tcgen05|gemm_skinny|flash_tc|flash_fwd|decode_attn|rmsnorm|layernorm|rope_kv|gemv_kernel|splice|embed|argmax|vit_|im2col|elementwise" --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "rc=$?"; wc -l gpurun_out/launches.csv
 python scripts/launch_shares.py gpurun_out/launches.csv | head -n 24
 echo "=== ncu full: decode megakernel + prefill GEMM + tcgen05 attention (one process)"
