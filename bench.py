@@ -387,7 +387,9 @@ def run_ours(args):
         e2e = None
         if not args.no_e2e:
             def api_step():
-                return model.generate(ids_host, images=images_host, do_sample=False, max_new_tokens=N, use_cache=True)
+                # eos disabled (every run does exactly N steps; random-init logits can hit id 2 by chance)
+                return model.generate(ids_host, images=images_host, do_sample=False, max_new_tokens=N, use_cache=True,
+                                      eos_token_id=[])
             for _ in range(max(1, min(args.warmup, 2))):
                 api_step()
             torch.cuda.synchronize()

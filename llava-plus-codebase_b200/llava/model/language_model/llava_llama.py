@@ -339,22 +339,19 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         if streamer is not None:
             streamer.put(prompt.cpu())
 
-        fast = greedy and streamer is None and not stopping_criteria and not eos_ids
-        if fast:
+        pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
+        if greedy and streamer is None and not stopping_criteria:
+            # nobody observes individual steps: the loop stays on the device (one megakernel launch / graph replay per
+            # token, no host round trip) in chunks; eos is checked once per chunk on the host
             first = engine.argmax(logits)
-            if max_new_tokens > 1:
-                rest = engine.decode_greedy(kv, first, max_new_tokens - 1)
-                if prof: prof.mark("decode_greedy")
-                new_tokens = torch.cat([first.unsqueeze(0), rest.to(first.device)], dim=0).t()
-            else:
-                new_tokens = first.unsqueeze(1)
+            new_tokens = _greedy_chunked(engine, kv, first, max_new_tokens, eos_ids, pad)
+            if prof: prof.mark("decode_greedy")
             out = torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
             if prof: prof.mark("ids to host"); prof.report()
             return out
 
         out = prompt.clone()
         finished = torch.zeros(B, dtype=torch.bool)
-        pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
         for step in range(max_new_tokens):
             if greedy:
                 nxt = engine.argmax(logits)
@@ -414,6 +411,41 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
 
     def eval(self):
         return super().eval()
+
+
+def _greedy_chunked(engine, kv, first, max_new_tokens, eos_ids, pad, chunk=16):
+    """Greedy decoding without per-step observers, equivalent to the per-step loop in generate(): `first` (int32 device
+    tensor [B]) is the token chosen from the prefill logits; further tokens come from engine.decode_greedy in chunks of
+    `chunk` steps (device-resident token feedback). After every chunk the host scans for eos: a finished row shows `pad`
+    from then on, generation stops at the step where every row has finished (the device may have run up to chunk-1 steps
+    past it; they are discarded — rows of a batch never interact, so unfinished rows are unaffected by what finished rows
+    were fed). With no eos ids this is a single chunk. Returns a CPU int64 tensor [B, n], 1 <= n <= max_new_tokens."""
+    B = int(first.numel())
+    finished = torch.zeros(B, dtype=torch.bool)
+    cols = []
+
+    def push(col):
+        col = torch.where(finished, torch.full_like(col, pad), col)
+        cols.append(col)
+        for b in range(B):
+            if int(col[b]) in eos_ids:
+                finished[b] = True
+        return bool(eos_ids) and bool(finished.all())
+
+    stop = push(first.to("cpu", torch.long))
+    done, last = 1, first
+    step = chunk if eos_ids else max_new_tokens
+    while not stop and done < max_new_tokens:
+        n = min(step, max_new_tokens - done)
+        rest = engine.decode_greedy(kv, last, n)          # [n, B] on the device
+        rest_cpu = rest.to("cpu", torch.long)
+        for i in range(n):
+            done += 1
+            if push(rest_cpu[i]):
+                stop = True
+                break
+        last = rest[n - 1]
+    return torch.stack(cols, dim=1)
 
 
 class _StageTimer:
