@@ -896,8 +896,9 @@ int b2_kv_reset(b2_kv* kv) {
     B2_CHECK_ARG(kv != nullptr, "b2_kv_reset: null");
     std::lock_guard<std::mutex> lk(kv->m->mu);
     DeviceGuard dg(kv->m->device);
-    B2_CUDA_CHECK(cudaMemset(kv->len_dev.p, 0, (size_t)kv->max_batch * 4));
-    B2_CUDA_CHECK(cudaMemset(kv->step_counter.p, 0, 4));
+    // Host bookkeeping only. The device-side lengths are rewritten by the next b2_prefill and the step counter by the next
+    // decode call, both on the CALLER's stream; a cudaMemset here would run on the legacy stream, unordered against work
+    // still in flight on a non-blocking caller stream (e.g. two forward() calls issued back to back).
     kv->len_host.assign(kv->max_batch, 0);
     return 0;
 }
