@@ -69,3 +69,43 @@ def test_empty_and_ragged_rows():
     assert lens == [6, 6]  # 2 text + 4 feature rows
     assert (src[1] == np.array([1, -5, -6, -7, -8, 9])).all()  # second slot: rows 4..7 -> -(r)-1
     assert m.all() and (pos[1] == np.arange(6)).all()
+
+
+def _random_case(rng, B, P, n_feat_rows_per_slot):
+    """Random batch in the reference's input format: ragged rows (attention_mask), 0..3 <image> per row, labels."""
+    Lt = int(rng.integers(3, 14))
+    ids = rng.integers(3, 90, size=(B, Lt)).astype(np.int64)
+    mask = np.zeros((B, Lt), dtype=bool)
+    slots = 0
+    for b in range(B):
+        n = int(rng.integers(1, Lt + 1))
+        mask[b, :n] = True
+        k = int(rng.integers(0, 4))
+        where = rng.choice(n, size=min(k, n), replace=False)
+        ids[b, where] = O.IMAGE_TOKEN_INDEX
+        slots += max(len(where), 1)  # a row without <image> still consumes one slot (SURVEY App. C.2)
+    labels = rng.integers(0, 90, size=(B, Lt)).astype(np.int64)
+    feats = [rng.standard_normal((n_feat_rows_per_slot, 8)).astype(np.float32) for _ in range(slots)]
+    return ids, mask, labels, feats
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_source_index_fuzz_against_the_restatement(seed):
+    """Randomised batches through build_source_index + emulated gather vs oracle.prepare_multimodal (itself pinned to the
+    unmodified reference by tests/test_oracle_golden.py): embeddings, mask, position ids, labels and lengths must be
+    identical for both padding sides, with and without truncation."""
+    rng = np.random.default_rng(seed)
+    B, P = int(rng.integers(1, 5)), int(rng.integers(1, 6))
+    ids, mask, labels, feats = _random_case(rng, B, P, P)
+    table = rng.standard_normal((100, 8)).astype(np.float32)
+    w = {"model.embed_tokens.weight": torch.from_numpy(table)}
+    side = "left" if seed % 2 else "right"
+    max_len = None if seed % 3 else int(rng.integers(2, 12))
+    want_e, want_m, want_p, want_l = O.prepare_multimodal(
+        w, torch.from_numpy(ids), None, {}, attention_mask=torch.from_numpy(mask), labels=torch.from_numpy(labels),
+        padding_side=side, max_length=max_len, image_features=[torch.from_numpy(f) for f in feats])
+    src, new_labels, m, pos, lens = build_source_index(ids, mask, labels, len(feats) * P, [P] * len(feats), max_len, side)
+    emb = _emulate_gather(src, table, np.concatenate(feats, 0))
+    np.testing.assert_array_equal(emb, want_e.numpy())
+    assert (m == want_m.numpy()).all() and (pos == want_p.numpy()).all() and (new_labels == want_l.numpy()).all()
+    assert lens == [int(x) for x in want_m.sum(1)]
