@@ -109,3 +109,24 @@ def test_source_index_fuzz_against_the_restatement(seed):
     np.testing.assert_array_equal(emb, want_e.numpy())
     assert (m == want_m.numpy()).all() and (pos == want_p.numpy()).all() and (new_labels == want_l.numpy()).all()
     assert lens == [int(x) for x in want_m.sum(1)]
+
+
+def test_source_index_equals_the_unmodified_reference_on_random_batches():
+    """48 randomised batches (ragged rows, 0-3 <image> per row, labels, both padding sides, truncation) run through the
+    UNMODIFIED reference prepare_inputs_labels_for_multimodal (tests/golden/make_splice_fuzz.py): the reference's output
+    embeddings, stored as a row-matched source index, its mask, position ids and labels must be reproduced exactly."""
+    g = np.load(os.path.join(GOLD, "tiny_splice_fuzz.npz"))
+    n = int(g["n_cases"])
+    assert n >= 40
+    for c in range(n):
+        ids, mask, labels = g[f"c{c}_ids"], g[f"c{c}_mask"].astype(bool), g[f"c{c}_labels"]
+        side = "left" if int(g[f"c{c}_left"]) else "right"
+        max_len = int(g[f"c{c}_maxlen"]) or None
+        slots, P = int(g[f"c{c}_slots"]), int(g[f"c{c}_P"])
+        src, new_labels, m, pos, lens = build_source_index(ids, mask, labels, slots * P, [P] * slots, max_len, side)
+        want = g[f"c{c}_src"]
+        assert src.shape == want.shape, (c, src.shape, want.shape)
+        assert (src.astype(np.int64) == want).all(), f"case {c}: source index differs from the reference"
+        assert (m == g[f"c{c}_omask"].astype(bool)).all() and (pos == g[f"c{c}_opos"]).all(), f"case {c}"
+        assert (new_labels == g[f"c{c}_olabels"]).all(), f"case {c}"
+        assert lens == [int(x) for x in g[f"c{c}_omask"].astype(bool).sum(1)]
