@@ -60,6 +60,16 @@ typedef struct b2_model_desc {
     int32_t max_images;       /* images encoded per ViT pass (larger batches are chunked) */
 } b2_model_desc;
 
+/* Token selection of the decode loop (HF GenerationMixin as the reference calls it: llava/serve/model_worker.py:155-185
+ * passes do_sample / temperature / top_p; top_k comes from the GenerationConfig default). do_sample == 0 -> greedy argmax. */
+typedef struct b2_sampling {
+    int32_t do_sample;
+    float temperature;        /* > 0 */
+    float top_p;              /* (0, 1]; 1 = off */
+    int32_t top_k;            /* 0 = off */
+    unsigned long long seed;  /* Philox key; draw t of row b is a pure function of (logits, seed, t, b) */
+} b2_sampling;
+
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
 int b2_init(int device);                 /* cudaSetDevice + capability check (needs sm_100) */
 const char* b2_last_error(void);         /* thread-local message of the last failing call */
@@ -103,8 +113,16 @@ int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* st
 /* The device half of prepare_inputs_labels_for_multimodal (reference llava_arch.py:150-225). src_index[r]
  * (device int32, one per output row of the padded [B,S] layout) is: >= 0 -> embed_tokens row (token id);
  * < 0 and != INT32_MIN -> row (-src-1) of image_feats [n_img*P, hidden]; INT32_MIN -> zero row (padding).
- * The index is built on the host from input_ids (llava/model/llava_arch.py in this repo). */
-int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, int rows, void* embeds_out, void* stream);
+ * The index is built on the host from input_ids (llava/model/llava_arch.py in this repo). image_feats holds n_feat_rows
+ * rows (0 with a NULL pointer for text-only batches). An index outside the embedding table or the feature rows never reads
+ * out of bounds: the row is zero-filled and the problem is reported by b2_async_error(). */
+int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, int n_feat_rows, int rows, void* embeds_out,
+              void* stream);
+/* Input problems that only a kernel can see (ids live on the device): returns in *code_out the OR of 1 = token id outside
+ * [0, vocab) or an image placeholder without features, 2 = image-feature row out of range, 4 = more placeholders than
+ * images, accumulated since the last call, and clears it. Meaningful after the stream has been synchronised (the codes
+ * are written to mapped host memory by the kernels); b2_last_error() then holds the text. */
+int b2_async_error(b2_model* m, int* code_out);
 /* LlamaModel.forward prefill over inputs_embeds [B,S,hidden] (HF modeling_llama.py:375-425 and :303-332 per
  * layer), right-padded rows with seq_lens_host[b] valid tokens (NULL => all S). Fills the KV cache from
  * position 0. logits_out: B2_LOGITS_LAST -> fp32 [B,vocab] at each sample's last valid position;
@@ -123,6 +141,21 @@ int b2_decode_step(b2_model* m, b2_kv* kv, const int32_t* tokens, int B, void* l
 int b2_decode_greedy(b2_model* m, b2_kv* kv, const int32_t* first_tokens, int B, int n_steps, int32_t* out_tokens,
                      void* stream);
 int b2_argmax(const float* logits, int B, int V, int32_t* out, void* stream);
+
+/* Streaming decode — what generate() needs when somebody watches every token (the reference always passes a streamer and a
+ * stopping criterion: llava/serve/model_worker.py:166-188, llava/serve/cli.py:91-102). The device loop is the same as
+ * b2_decode_greedy (token feedback stays on the device, argmax or the temperature/top-k/top-p draw is a kernel), but every
+ * step also publishes its token into a ring in mapped pinned host memory, tagged with the generation's epoch, so the host
+ * reads token t while step t+k is already running: no D2H copy and no stream synchronisation per token.
+ *   b2_stream_begin   selects token 0 from `logits` (device fp32 [B,vocab], the prefill's last-position logits) and
+ *                     publishes it as index 0;
+ *   b2_stream_enqueue queues n_steps more decode steps (token indices continue from the last one scheduled);
+ *   b2_stream_wait    blocks until token `index` is visible and copies it to tokens_host[B] (host). Takes no lock;
+ *                     timeout_ms <= 0 waits forever; -3 on timeout, -2 if the device faulted.
+ * Steps that were queued past the point where the host decides to stop simply run to completion (rows never interact). */
+int b2_stream_begin(b2_model* m, b2_kv* kv, const float* logits, int B, const b2_sampling* sampling, void* stream);
+int b2_stream_enqueue(b2_model* m, b2_kv* kv, int n_steps, void* stream);
+int b2_stream_wait(b2_kv* kv, int index, int32_t* tokens_host, int timeout_ms);
 
 /* ---- single-kernel entry points (unit-level parity tests; same kernels the hot path launches) ----------- */
 int b2_op_gemm(const void* A, int lda, const void* W, int ldw, const void* bias, const void* residual, int ld_res,
@@ -164,6 +197,9 @@ int b2_op_decode_attn(const void* qkv, void* kcache, void* vcache, const int32_t
 int64_t b2_op_decode_attn_scratch_bytes(int B, int H, int nsplit); /* caller zero-fills the scratch once */
 int b2_op_interleave_gate_up(const void* gate, const void* up, void* out, int I, int h, void* stream);
 int b2_op_im2col(const void* pixels, void* out, int B, int img, int patch, int kpad, void* stream);
+/* one selection per row from fp32 logits [B,V] (csrc/sampling.cu): out_tokens device int32 [B]; `index` is the draw index
+ * that keys the Philox stream (token position within a generation). Synchronises the stream. */
+int b2_op_sample(const float* logits, int B, int V, const b2_sampling* sampling, int index, int32_t* out_tokens, void* stream);
 
 #ifdef __cplusplus
 }

@@ -764,6 +764,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                 p.tok[b] = tk;
                 p.out_tokens[(size_t)(*p.step_counter) * B + b] = tk;
                 p.cur_len[b] += 1;  // every attention phase of this launch is behind the last barrier
+                if (p.ring != nullptr) {  // streaming generate(): the host reads the token from mapped pinned memory
+                    const int pub = p.sstate->pub_counter, tag = p.sstate->tag;
+                    if (tag != 0) {
+                        reinterpret_cast<volatile int32_t*>(p.ring)[(size_t)(pub % p.ring_cap) * B + b] = (tag << 20) | (tk & 0xFFFFF);
+                        __threadfence_system();
+                    }
+                }
             }
         }
     }
@@ -774,6 +781,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
         if (atomicAdd(p.done_count, 1u) == gridDim.x - 1) {
             *p.done_count = 0u;
             *p.step_counter += 1;
+            if (p.ring != nullptr) p.sstate->pub_counter += 1;
         }
     }
 }

@@ -143,18 +143,49 @@ struct MegaParams {
     int l2_mode = 1;        // 1 = prefetch.global.L2 lines (LSU), 2 = cp.async.bulk.prefetch.L2 (TMA queue)
     int fast_prologue = 0;  // single-pass activation staging with pre-barrier RMSNorm-weight loads
     long long* trace = nullptr;  // optional [n_phases+2][4] SM-clock timestamps of CTA 0 (B2_MEGA_TRACE=1)
+    // token publication to the host ring (sampling.cu): non-null only for greedy streaming; with do_sample the separate
+    // sample_publish kernel that follows the launch overrides the fused argmax and publishes instead
+    struct SampleState* sstate = nullptr;
+    int32_t* ring = nullptr;
+    int ring_cap = 0;
 };
 // one launch = embed -> all layers -> lm_head -> argmax -> token store; cur_len/step_counter advance on device
 int decode_mega(const MegaParams& p, cudaStream_t stream);
 bool decode_mega_fits(int B, int h, int I);
 
+// ---- token selection + host-ring publication (sampling.cu) --------------------------------------------------
+// Device-resident state of one generation (lives in the b2_kv): read by the kernels, so a captured CUDA graph of the decode
+// step stays valid when the sampling parameters change.
+struct SampleState {
+    int do_sample;            // 0 = greedy argmax
+    float temperature, top_p;
+    int top_k;                // 0 = off
+    unsigned long long seed;  // Philox key
+    int tag;                  // generation epoch 1..2047 published with every token; 0 = do not publish to the host ring
+    int pub_counter;          // index of the next token of this generation
+    unsigned int done;        // rows finished in the current launch (self-resetting)
+};
+enum { SP_SELECT = 1,     // choose from `logits` (argmax or sample) and write tok[b]; otherwise tok[b] is already chosen
+       SP_WRITE_OUT = 2,  // out_tokens[(*step_counter + step_offset) * B + b] = token
+       SP_BUMP = 4 };     // last row: *step_counter += 1, cur_len[b] += 1
+int sample_state_set(SampleState* st_dev, const SampleState& v, cudaStream_t stream);
+int sample_publish(const float* logits, int V, int B, SampleState* st_dev, int32_t* tok, int32_t* out_tokens,
+                   int32_t* step_counter, int32_t* cur_len, int32_t* ring_dev, int ring_cap, int flags, int step_offset,
+                   cudaStream_t stream);
+
 // ---- misc (misc_ops.cu) ----------------------------------------------------------------------------
-// out[r, :] = src_index[r] >= 0 ? table[src_index[r]] : (src_index[r] == INT32_MIN ? 0 : feats[-src_index[r]-1])
-int splice_embed(const int32_t* src_index, const void* table, const void* feats, void* out, int rows, int h,
+// out[r, :] = src_index[r] >= 0 ? table[src_index[r]] : (src_index[r] == INT32_MIN ? 0 : feats[-src_index[r]-1]).
+// Rows whose index is outside [0, vocab) / [0, n_feat_rows) are written as zeros and reported through *err_flag
+// (mapped host memory, B2_ERR_* codes, may be null): nothing is ever read out of bounds.
+int splice_embed(const int32_t* src_index, const void* table, const void* feats, void* out, int rows, int h, int vocab,
+                 int n_feat_rows, int* err_flag, cudaStream_t stream);
+int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab, int* err_flag,
                  cudaStream_t stream);
-int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab,
-                 cudaStream_t stream);
+enum { B2_ERR_TOKEN_RANGE = 1, B2_ERR_IMAGE_ROW_RANGE = 2, B2_ERR_SPLICE_SLOTS = 4 };
 int argmax_f32(const float* logits, int B, int V, int32_t* out, cudaStream_t stream);
+struct I32Pack { int32_t v[128]; };
+// dst_a[i] = a_host[i] (and dst_b[i] = b_host[i] when dst_b != null), i < n: values travel as kernel parameters
+int set_i32_pairs(int32_t* dst_a, const int32_t* a_host, int32_t* dst_b, const int32_t* b_host, int n, cudaStream_t stream);
 int add_i32(int32_t* x, int n, int delta, cudaStream_t stream);
 int convert_to_bf16(const void* src, int src_dtype, void* dst, int64_t n, cudaStream_t stream);
 // out[2I, h]: within each 128-row group g: rows [0,64) = gate[g*64 .. +64), rows [64,128) = up[g*64 .. +64)

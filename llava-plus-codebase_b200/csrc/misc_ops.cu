@@ -15,24 +15,42 @@
 namespace b2 {
 namespace {
 
+// err_flag points at int[8] in mapped host memory: slot log2(code) is set to 1 with a plain store (no PCIe atomics needed)
+__device__ __forceinline__ void report_err(int* err_flag, int code) {
+    reinterpret_cast<volatile int*>(err_flag)[31 - __clz(code)] = 1;
+}
+
+// An index outside the embedding table / the image-feature rows (tokenizer larger than the table, a leftover
+// IMAGE_TOKEN_INDEX with no images, ...) must neither read out of bounds nor kill the context: the row becomes zeros and the
+// code is flagged in err_flag[] (mapped host memory), which the host turns into a ValueError at its next sync point.
 __global__ void splice_embed_kernel(const int32_t* __restrict__ src_index, const uint4* __restrict__ table,
-                                    const uint4* __restrict__ feats, uint4* __restrict__ out, int vec_per_row) {
+                                    const uint4* __restrict__ feats, uint4* __restrict__ out, int vec_per_row, int vocab,
+                                    int n_feat_rows, int* err_flag) {
     const int row = blockIdx.x;
     const int32_t s = src_index[row];
     uint4* o = out + (size_t)row * vec_per_row;
-    if (s == INT_MIN) {
+    const uint4* src = nullptr;
+    if (s >= 0) {
+        if (s < vocab) src = table + (size_t)s * vec_per_row;
+        else if (threadIdx.x == 0 && err_flag) report_err(err_flag, B2_ERR_TOKEN_RANGE);
+    } else if (s != INT_MIN) {
+        const int64_t f = -(int64_t)s - 1;
+        if (feats != nullptr && f < n_feat_rows) src = feats + (size_t)f * vec_per_row;
+        else if (threadIdx.x == 0 && err_flag) report_err(err_flag, feats == nullptr ? B2_ERR_TOKEN_RANGE : B2_ERR_IMAGE_ROW_RANGE);
+    }
+    if (src == nullptr) {
         for (int c = threadIdx.x; c < vec_per_row; c += blockDim.x) o[c] = make_uint4(0, 0, 0, 0);
     } else {
-        const uint4* src = s >= 0 ? table + (size_t)s * vec_per_row : feats + (size_t)(-(int64_t)s - 1) * vec_per_row;
         for (int c = threadIdx.x; c < vec_per_row; c += blockDim.x) o[c] = src[c];
     }
 }
 
 __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const uint4* __restrict__ table,
-                                    uint4* __restrict__ out, int vec_per_row, int vocab) {
+                                    uint4* __restrict__ out, int vec_per_row, int vocab, int* err_flag) {
     const int row = blockIdx.x;
     int32_t t = tokens[row];
-    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);  // never read out of bounds; ids are validated on the host
+    if ((t < 0 || t >= vocab) && threadIdx.x == 0 && err_flag) report_err(err_flag, B2_ERR_TOKEN_RANGE);
+    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);  // never read out of bounds
     const uint4* src = table + (size_t)t * vec_per_row;
     uint4* o = out + (size_t)row * vec_per_row;
     for (int c = threadIdx.x; c < vec_per_row; c += blockDim.x) o[c] = src[c];
@@ -110,23 +128,41 @@ __global__ void store_token_kernel(const int32_t* __restrict__ src, int32_t* __r
     if (b < B) dst_base[(size_t)(*step_counter) * B + b] = src[b];
 }
 
+// dst_a[off + i] = a.v[i], dst_b[off + i] = b.v[i]: small host vectors travel as kernel parameters (no pinned staging
+// buffer whose lifetime would force a stream sync in the caller)
+__global__ void set_i32_pairs_kernel(int32_t* dst_a, int32_t* dst_b, I32Pack a, I32Pack b, int n, int off) {
+    const int i = threadIdx.x;
+    if (i < n) { dst_a[off + i] = a.v[i]; if (dst_b) dst_b[off + i] = b.v[i]; }
+}
+
 }  // namespace
 
-int splice_embed(const int32_t* src_index, const void* table, const void* feats, void* out, int rows, int h,
-                 cudaStream_t stream) {
+int set_i32_pairs(int32_t* dst_a, const int32_t* a_host, int32_t* dst_b, const int32_t* b_host, int n, cudaStream_t stream) {
+    for (int off = 0; off < n; off += 128) {
+        const int c = n - off < 128 ? n - off : 128;
+        I32Pack pa, pb;
+        for (int i = 0; i < c; ++i) { pa.v[i] = a_host[off + i]; pb.v[i] = b_host ? b_host[off + i] : 0; }
+        set_i32_pairs_kernel<<<1, 128, 0, stream>>>(dst_a, dst_b, pa, pb, c, off);
+        B2_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int splice_embed(const int32_t* src_index, const void* table, const void* feats, void* out, int rows, int h, int vocab,
+                 int n_feat_rows, int* err_flag, cudaStream_t stream) {
     B2_CHECK_ARG(h % 8 == 0 && rows > 0, "splice_embed: bad shape rows=%d h=%d", rows, h);
     splice_embed_kernel<<<rows, 128, 0, stream>>>(src_index, reinterpret_cast<const uint4*>(table),
                                                   reinterpret_cast<const uint4*>(feats),
-                                                  reinterpret_cast<uint4*>(out), h / 8);
+                                                  reinterpret_cast<uint4*>(out), h / 8, vocab, n_feat_rows, err_flag);
     B2_LAUNCH_CHECK();
     return 0;
 }
 
-int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab,
+int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab, int* err_flag,
                  cudaStream_t stream) {
     B2_CHECK_ARG(h % 8 == 0 && rows > 0, "embed_tokens: bad shape rows=%d h=%d", rows, h);
     embed_tokens_kernel<<<rows, 128, 0, stream>>>(tokens, reinterpret_cast<const uint4*>(table),
-                                                  reinterpret_cast<uint4*>(out), h / 8, vocab);
+                                                  reinterpret_cast<uint4*>(out), h / 8, vocab, err_flag);
     B2_LAUNCH_CHECK();
     return 0;
 }

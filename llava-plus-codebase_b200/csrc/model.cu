@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <mutex>
 #include <string>
@@ -57,9 +58,11 @@ struct DevBuf {
 
 struct VitLayer {
     DevBuf ln1_g, ln1_b, wqkv, bqkv, wo, bo, ln2_g, ln2_b, w1, b1, w2, b2;
+    unsigned qkv_w = 0, qkv_b = 0;  // bit j set: part j (q/k/v) of the fused buffer has arrived
 };
 struct LlamaLayer {
     DevBuf ln1, wqkv, wo, ln2, wgu, wd;
+    unsigned qkv_parts = 0;
     DevBuf wqkv8, wo8, wgu8, wd8, s_qkv, s_o, s_gu, s_d;  // e4m3 copies + per-row fp32 scales (b2_model_enable_fp8_decode)
     DevBuf tmp_gate, tmp_up;  // staging until both halves arrived
     bool has_gate = false, has_up = false;
@@ -82,7 +85,14 @@ struct b2_model {
     DevBuf p0_w, p0_b, p2_w, p2_b;
     DevBuf embed, final_norm, lm_head;
     std::vector<LlamaLayer> ll;
-    std::vector<std::string> seen;  // keys received (finalize checks completeness)
+    // errors detected by kernels (bad token ids / image rows): int[8] in mapped pinned host memory, slot = log2(B2_ERR_*)
+    int* err_host = nullptr;
+    int* err_dev = nullptr;
+    // the workspaces below are shared by every call on this model: a call on stream B must not start before the previous
+    // call's kernels on stream A are done with them (calls on one stream are ordered anyway)
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_valid = false;
     // ViT workspace (per chunk of max_images)
     DevBuf v_col, v_patch, v_hidden, v_xn, v_qkv, v_attn, v_mlp, v_feats, p_mid;
     // LLaMA workspace
@@ -110,6 +120,15 @@ struct b2_kv {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int warm_B = 0;  // an eager step has run for this B (function attributes set, driver entry points resolved)
+    // token selection state (sampling.cu) + the host-visible token ring of the streaming decode API
+    DevBuf sstate;                 // SampleState on the device
+    SampleState samp_host = {};    // what was last written there (pub_counter / done excluded: the device advances them)
+    bool samp_valid = false;
+    int32_t* ring_host = nullptr;  // cudaHostAlloc(mapped) [ring_cap][max_batch]; entry = tag << 20 | token
+    int32_t* ring_dev = nullptr;
+    int ring_cap = 0;
+    int epoch = 0;                 // generations started on this cache (tag = 1 + epoch % 2047)
+    int stream_B = 0, stream_tag = 0, stream_scheduled = 0;  // streaming generation in progress: tokens scheduled so far
     size_t layer_stride() const { return (size_t)max_batch * m->d.heads * max_seq * m->hd; }
 };
 
@@ -279,10 +298,15 @@ int set_vision_weight(b2_model* m, const std::string& k, const void* ptr, const 
             if (starts_with(s, names[j])) {
                 if (s == std::string(names[j]) + "weight") {
                     B2_TRY(expect_shape(key, shape, ndim, D, D));
-                    return put(L.wqkv, (size_t)3 * D * D, (size_t)j * D * D, ptr, dt, (int64_t)D * D);
+                    B2_TRY(put(L.wqkv, (size_t)3 * D * D, (size_t)j * D * D, ptr, dt, (int64_t)D * D));
+                    L.qkv_w |= 1u << j;
+                    return 0;
                 }
+                if (s != std::string(names[j]) + "bias") break;
                 B2_TRY(expect_shape(key, shape, ndim, D));
-                return put(L.bqkv, (size_t)3 * D, (size_t)j * D, ptr, dt, D);
+                B2_TRY(put(L.bqkv, (size_t)3 * D, (size_t)j * D, ptr, dt, D));
+                L.qkv_b |= 1u << j;
+                return 0;
             }
         }
         if (s == "self_attn.out_proj.weight") { B2_TRY(expect_shape(key, shape, ndim, D, D)); return put(L.wo, (size_t)D * D, 0, ptr, dt, (int64_t)D * D); }
@@ -306,7 +330,9 @@ int set_llama_layer_weight(b2_model* m, int li, const std::string& s, const char
     for (int j = 0; j < 3; ++j) {
         if (s == names[j]) {
             B2_TRY(expect_shape(key, shape, ndim, h, h));
-            return put(L.wqkv, (size_t)3 * h * h, (size_t)j * h * h, ptr, dt, (int64_t)h * h);
+            B2_TRY(put(L.wqkv, (size_t)3 * h * h, (size_t)j * h * h, ptr, dt, (int64_t)h * h));
+            L.qkv_parts |= 1u << j;
+            return 0;
         }
     }
     if (s == "self_attn.o_proj.weight") { B2_TRY(expect_shape(key, shape, ndim, h, h)); return put(L.wo, (size_t)h * h, 0, ptr, dt, (int64_t)h * h); }
@@ -387,7 +413,7 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const b2_model_desc& d = m->d;
     const int h = d.hidden, I = d.inter, H = d.heads, V = d.vocab;
     const int nsplit = decode_nsplit(B, H);
-    B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, st));
+    B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, m->err_dev, st));
     // batch <= 8: tensor-core GEMV kernels (falls back to the skinny-M tcgen05 GEMM when the activations do not fit smem)
     // batch 7..128: swap-AB stream-K GEMM (weights streamed once, all SMs busy); otherwise GEMV kernels (B <= 8) or
     // the tile GEMM
@@ -459,10 +485,11 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
         B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, B, h, d.rms_eps, st));
         B2_TRY(gemm(m->xn.p, h, m->lm_head.p, h, nullptr, nullptr, 0, m->logits.p, V, 1, B, V, h, ACT_NONE, st));
     }
-    B2_TRY(argmax_f32(m->logits.as<float>(), B, V, kv->tok.as<int32_t>(), st));
-    B2_TRY(store_token(kv->tok.as<int32_t>(), kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), B, st));
-    B2_TRY(add_i32(kv->step_counter.as<int32_t>(), 1, 1, st));
-    B2_TRY(add_i32(kv->len_dev.as<int32_t>(), B, 1, st));
+    // argmax or temperature/top-k/top-p draw (device-resident SampleState), token feedback, host-ring publication and the
+    // step / cache-length counters in ONE launch (was: argmax + store_token + 2 x add_i32)
+    B2_TRY(sample_publish(m->logits.as<float>(), V, B, kv->sstate.as<SampleState>(), kv->tok.as<int32_t>(),
+                          kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), kv->len_dev.as<int32_t>(),
+                          kv->ring_dev, kv->ring_cap, SP_SELECT | SP_WRITE_OUT | SP_BUMP, 0, st));
     return 0;
 }
 
@@ -520,6 +547,10 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     kv->mega_bar_base += (unsigned int)(5 * d.layers + 2) * (unsigned int)num_sms();
     p.eps = d.rms_eps; p.theta = d.rope_theta;
     p.scale_log2 = (1.0f / sqrtf((float)m->hd)) * 1.4426950408889634f;
+    // greedy streaming: the kernel's fused argmax publishes to the host ring itself; with do_sample the sample_publish
+    // launch below overrides the fused argmax (token feedback, out_tokens slot) and publishes instead
+    const bool sampling = kv->samp_host.do_sample != 0;
+    if (!sampling && kv->samp_host.tag != 0) { p.sstate = kv->sstate.as<SampleState>(); p.ring = kv->ring_dev; p.ring_cap = kv->ring_cap; }
     {   // tuning knobs, re-read every launch so a sweep can flip them inside one process (scripts/mega_sweep.py)
         const char* e = getenv("B2_MEGA_L2_AHEAD");
         int ahead = e ? atoi(e) : kMegaL2AheadDefault;
@@ -555,7 +586,12 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
             return r;
         }
     }
-    return decode_mega(p, st);
+    B2_TRY(decode_mega(p, st));
+    if (sampling)
+        B2_TRY(sample_publish(m->logits.as<float>(), d.vocab, B, kv->sstate.as<SampleState>(), kv->tok.as<int32_t>(),
+                              kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), kv->len_dev.as<int32_t>(),
+                              kv->ring_dev, kv->ring_cap, SP_SELECT | SP_WRITE_OUT, -1, st));
+    return 0;
 }
 
 int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
@@ -584,17 +620,37 @@ int decode_step_run(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
         kv->graph_B = B;
     }
     B2_CUDA_CHECK(cudaGraphLaunch(kv->graph, st));
-    // kernels per step: embed + L*(qkv, attn, o, gate/up, down [+2 norms when B>8]) + head(+norm) + argmax + 3
+    // kernels per step: embed + L*(qkv, attn, o, gate/up, down [+2 norms when B>8]) + head(+norm) + sample_publish
     const bool small = !use_skinny(kv, B) && B <= 8 && gemv_fits(B, m->d.hidden, m->d.inter, ACT_NONE) &&
                        gemv_fits(B, m->d.vocab, m->d.hidden, ACT_NONE);
     const int per_layer = small ? 5 : ((m->fp8_decode && use_skinny(kv, B)) ? 9 : 7);
-    g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (small ? 1 : 2) + 4;
+    g_launch_count += 1 + (unsigned long long)m->d.layers * per_layer + (small ? 1 : 2) + 1;
     return 0;
 }
 
+// makes `dev` current for the duration of an ABI call and restores the caller's device afterwards
 struct DeviceGuard {
-    explicit DeviceGuard(int dev) { cudaSetDevice(dev); }
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
+
+// Cross-stream ordering of the shared model workspaces (see b2_model::ws_event). Caller holds the model lock.
+int ws_enter(b2_model* m, cudaStream_t st) {
+    if (m->ws_valid && m->ws_stream != st) B2_CUDA_CHECK(cudaStreamWaitEvent(st, m->ws_event, 0));
+    return 0;
+}
+int ws_leave(b2_model* m, cudaStream_t st) {
+    B2_CUDA_CHECK(cudaEventRecord(m->ws_event, st));
+    m->ws_stream = st;
+    m->ws_valid = true;
+    return 0;
+}
 
 }  // namespace
 
@@ -694,7 +750,6 @@ int b2_model_set_weight(b2_model* m, const char* hf_key, const void* ptr, const 
         set_error("set_weight: unknown key '%s'", hf_key);
         return -1;
     }
-    if (r == 0) m->seen.push_back(k);
     return r;
 }
 
@@ -729,20 +784,24 @@ int b2_model_finalize(b2_model* m) {
         set_error("b2_model_finalize: missing weights: %s", missing.c_str());
         return -3;
     }
-    // q/k/v (and fused tensors filled piecewise) must each have received all parts: count keys
-    // (a partially filled fused buffer would contain uninitialised memory)
-    {
-        size_t want = 5 + m->vit.size() * 16 + 4 + 3 + m->ll.size() * 9;
-        size_t have = 0;
-        for (const std::string& k : m->seen)
-            if (k.find("post_layernorm") == std::string::npos && k.find("position_ids") == std::string::npos &&
-                k.find("inv_freq") == std::string::npos)
-                have++;
-        // keys for dead vision layers are accepted but not counted precisely; only flag clear shortfalls
-        if (have < want) {
-            set_error("b2_model_finalize: received %zu tensors, expected at least %zu", have, want);
+    // fused buffers are filled piecewise (q/k/v): every part must have arrived, or the buffer holds uninitialised memory
+    // (gate/up is only materialised once both halves are there, so its pointer check above is already exact)
+    for (size_t i = 0; i < m->vit.size(); ++i)
+        if (m->vit[i].qkv_w != 7u || m->vit[i].qkv_b != 7u) {
+            set_error("b2_model_finalize: vision layer %zu is missing q/k/v parts (weights mask %u, bias mask %u of 7)", i,
+                      m->vit[i].qkv_w, m->vit[i].qkv_b);
             return -3;
         }
+    for (size_t i = 0; i < m->ll.size(); ++i)
+        if (m->ll[i].qkv_parts != 7u) {
+            set_error("b2_model_finalize: decoder layer %zu is missing q/k/v projections (mask %u of 7)", i, m->ll[i].qkv_parts);
+            return -3;
+        }
+    if (m->err_host == nullptr) {
+        B2_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m->err_host), 8 * sizeof(int), cudaHostAllocMapped));
+        memset(m->err_host, 0, 8 * sizeof(int));
+        B2_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->err_dev), m->err_host, 0));
+        B2_CUDA_CHECK(cudaEventCreateWithFlags(&m->ws_event, cudaEventDisableTiming));
     }
     // workspaces
     const int D = d.vit_hidden, I = d.vit_inter, h = d.hidden;
@@ -771,8 +830,10 @@ int b2_model_finalize(b2_model* m) {
 
 int b2_model_destroy(b2_model* m) {
     if (m == nullptr) return 0;
-    cudaSetDevice(m->device);
+    DeviceGuard dg(m->device);
     cudaDeviceSynchronize();
+    if (m->err_host) cudaFreeHost(m->err_host);
+    if (m->ws_event) cudaEventDestroy(m->ws_event);
     DevBuf* top[] = {&m->patch_w, &m->cls, &m->pos, &m->pre_g, &m->pre_b, &m->p0_w, &m->p0_b, &m->p2_w, &m->p2_b,
                      &m->embed, &m->final_norm, &m->lm_head, &m->v_col, &m->v_patch, &m->v_hidden, &m->v_xn,
                      &m->v_qkv, &m->v_attn, &m->v_mlp, &m->v_feats, &m->p_mid, &m->x, &m->xn, &m->qkv, &m->attn,
@@ -881,6 +942,17 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
         }
         cudaMemset(kv->sk_counters.p, 0, gemm_skinny_counter_bytes(nmax));
     }
+    kv->ring_cap = max_seq;
+    if ((r = kv->sstate.alloc(sizeof(SampleState))) != 0) { b2_kv_destroy(kv); return r; }
+    cudaMemset(kv->sstate.p, 0, sizeof(SampleState));
+    if (cudaHostAlloc(reinterpret_cast<void**>(&kv->ring_host), (size_t)kv->ring_cap * max_batch * 4, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&kv->ring_dev), kv->ring_host, 0) != cudaSuccess) {
+        set_error("b2_kv_create: cannot allocate the pinned token ring (%d x %d)", kv->ring_cap, max_batch);
+        cudaGetLastError();
+        b2_kv_destroy(kv);
+        return -2;
+    }
+    memset(kv->ring_host, 0, (size_t)kv->ring_cap * max_batch * 4);
     cudaMemset(kv->k.p, 0, per);
     cudaMemset(kv->v.p, 0, per);
     cudaMemset(kv->len_dev.p, 0, (size_t)max_batch * 4);
@@ -905,14 +977,15 @@ int b2_kv_reset(b2_kv* kv) {
 
 int b2_kv_destroy(b2_kv* kv) {
     if (kv == nullptr) return 0;
-    cudaSetDevice(kv->m->device);
+    DeviceGuard dg(kv->m->device);
     cudaDeviceSynchronize();
+    if (kv->ring_host) cudaFreeHost(kv->ring_host);
     if (kv->graph) cudaGraphExecDestroy(kv->graph);
     if (kv->own_stream) cudaStreamDestroy(kv->own_stream);
     if (kv->ev_fork) cudaEventDestroy(kv->ev_fork);
     if (kv->ev_join) cudaEventDestroy(kv->ev_join);
     DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
-                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters};
+                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters, &kv->sstate};
     for (DevBuf* b : bs) b->free();
     delete kv;
     return 0;
@@ -931,13 +1004,14 @@ int b2_vit_encode(b2_model* m, const void* pixels, int B, void* out_feats, void*
     std::lock_guard<std::mutex> lk(m->mu);
     DeviceGuard dg(m->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(ws_enter(m, st));
     const size_t img_elems = (size_t)3 * m->d.image_size * m->d.image_size;
     for (int b0 = 0; b0 < B; b0 += m->d.max_images) {
         const int n = B - b0 < m->d.max_images ? B - b0 : m->d.max_images;
         B2_TRY(vit_forward_chunk(m, reinterpret_cast<const bf16*>(pixels) + b0 * img_elems, n,
                                  reinterpret_cast<bf16*>(out_feats) + (size_t)b0 * m->P * m->d.vit_hidden, st));
     }
-    return 0;
+    return ws_leave(m, st);
 }
 
 int b2_project(b2_model* m, const void* feats, int rows, void* out, void* stream) {
@@ -945,7 +1019,10 @@ int b2_project(b2_model* m, const void* feats, int rows, void* out, void* stream
     B2_CHECK_ARG(m->finalized, "b2_project: model not finalized");
     std::lock_guard<std::mutex> lk(m->mu);
     DeviceGuard dg(m->device);
-    return project_rows(m, feats, rows, out, reinterpret_cast<cudaStream_t>(stream));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(ws_enter(m, st));
+    B2_TRY(project_rows(m, feats, rows, out, st));
+    return ws_leave(m, st);
 }
 
 int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* stream) {
@@ -954,6 +1031,7 @@ int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* st
     std::lock_guard<std::mutex> lk(m->mu);
     DeviceGuard dg(m->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(ws_enter(m, st));
     const size_t img_elems = (size_t)3 * m->d.image_size * m->d.image_size;
     for (int b0 = 0; b0 < B; b0 += m->d.max_images) {
         const int n = B - b0 < m->d.max_images ? B - b0 : m->d.max_images;
@@ -961,17 +1039,35 @@ int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* st
         B2_TRY(project_rows(m, m->v_feats.p, n * m->P,
                             reinterpret_cast<bf16*>(out) + (size_t)b0 * m->P * m->d.hidden, st));
     }
-    return 0;
+    return ws_leave(m, st);
 }
 
-int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, int rows, void* embeds_out,
+int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, int n_feat_rows, int rows, void* embeds_out,
               void* stream) {
-    B2_CHECK_ARG(m && src_index && embeds_out && rows >= 1, "b2_splice: bad argument");
+    B2_CHECK_ARG(m && src_index && embeds_out && rows >= 1 && n_feat_rows >= 0, "b2_splice: bad argument");
+    B2_CHECK_ARG(image_feats != nullptr || n_feat_rows == 0, "b2_splice: n_feat_rows=%d without image_feats", n_feat_rows);
     B2_CHECK_ARG(m->finalized, "b2_splice: model not finalized");
     std::lock_guard<std::mutex> lk(m->mu);
     DeviceGuard dg(m->device);
-    return splice_embed(src_index, m->embed.p, image_feats, embeds_out, rows, m->d.hidden,
-                        reinterpret_cast<cudaStream_t>(stream));
+    return splice_embed(src_index, m->embed.p, image_feats, embeds_out, rows, m->d.hidden, m->d.vocab, n_feat_rows,
+                        m->err_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_async_error(b2_model* m, int* code_out) {
+    B2_CHECK_ARG(m && code_out, "b2_async_error: null argument");
+    int code = 0;
+    if (m->err_host != nullptr)
+        for (int i = 0; i < 8; ++i)
+            if (reinterpret_cast<volatile int*>(m->err_host)[i] != 0) {
+                code |= 1 << i;
+                reinterpret_cast<volatile int*>(m->err_host)[i] = 0;
+            }
+    *code_out = code;
+    if (code != 0)
+        set_error("device-side input check failed:%s%s%s", (code & B2_ERR_TOKEN_RANGE) ? " token id outside [0, vocab) (or an image placeholder without image features)" : "",
+                  (code & B2_ERR_IMAGE_ROW_RANGE) ? " image-feature row outside the encoded images" : "",
+                  (code & B2_ERR_SPLICE_SLOTS) ? " more image placeholders than images" : "");
+    return 0;
 }
 
 int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_lens_host, int B, int S,
@@ -995,9 +1091,9 @@ int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_le
         B2_CHECK_ARG(lens[b] >= 1 && lens[b] <= S, "b2_prefill: seq_lens[%d]=%d out of range (S=%d)", b, lens[b], S);
         last[b] = b * S + lens[b] - 1;
     }
-    B2_CUDA_CHECK(cudaMemcpyAsync(kv->len_dev.p, lens.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-    B2_CUDA_CHECK(cudaMemcpyAsync(m->last_idx.p, last.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-    B2_CUDA_CHECK(cudaStreamSynchronize(st));  // lens/last are stack-backed host vectors
+    B2_TRY(ws_enter(m, st));
+    // lengths / last-row indices travel as kernel parameters: no pinned staging, no stream sync in this call
+    B2_TRY(set_i32_pairs(kv->len_dev.as<int32_t>(), lens.data(), m->last_idx.as<int32_t>(), last.data(), B, st));
     for (int b = 0; b < B; ++b) kv->len_host[b] = lens[b];
 
     B2_CUDA_CHECK(cudaMemcpyAsync(m->x.p, embeds, (size_t)T * h * 2, cudaMemcpyDeviceToDevice, st));
@@ -1033,12 +1129,35 @@ int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_le
         B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, T, h, d.rms_eps, st));
         B2_TRY(gemm(m->xn.p, h, m->lm_head.p, h, nullptr, nullptr, 0, logits_out, V, 1, T, V, h, ACT_NONE, st));
     }
-    return 0;
+    return ws_leave(m, st);
 }
 
 static int copy_tokens_in(b2_kv* kv, const int32_t* tokens, int B, cudaStream_t st) {
     B2_CUDA_CHECK(cudaMemcpyAsync(kv->tok.p, tokens, (size_t)B * 4, cudaMemcpyDefault, st));
     return 0;
+}
+
+// device-resident selection state := v (pub_counter restarts at 0); launched only when something changed
+static int set_sampling(b2_kv* kv, const SampleState& v, bool force, cudaStream_t st) {
+    const SampleState& c = kv->samp_host;
+    if (!force && kv->samp_valid && c.do_sample == v.do_sample && c.temperature == v.temperature && c.top_p == v.top_p &&
+        c.top_k == v.top_k && c.seed == v.seed && c.tag == v.tag)
+        return 0;
+    B2_TRY(sample_state_set(kv->sstate.as<SampleState>(), v, st));
+    kv->samp_host = v;
+    kv->samp_valid = true;
+    return 0;
+}
+static int set_greedy_unpublished(b2_kv* kv, cudaStream_t st) {
+    SampleState v = {};
+    v.temperature = 1.f; v.top_p = 1.f;
+    kv->stream_B = 0;  // any streaming generation on this cache is over
+    return set_sampling(kv, v, false, st);
+}
+static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
 int b2_decode_step(b2_model* m, b2_kv* kv, const int32_t* tokens, int B, void* logits_out, int32_t* next_tokens_out,
@@ -1053,8 +1172,10 @@ int b2_decode_step(b2_model* m, b2_kv* kv, const int32_t* tokens, int B, void* l
         B2_CHECK_ARG(kv->len_host[b] >= 1 && kv->len_host[b] < kv->max_seq,
                      "b2_decode_step: sample %d has cache length %d (capacity %d; prefill first)", b, kv->len_host[b],
                      kv->max_seq);
+    B2_TRY(ws_enter(m, st));
     B2_TRY(copy_tokens_in(kv, tokens, B, st));
     B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
+    B2_TRY(set_greedy_unpublished(kv, st));
     cudaStream_t run = nullptr;
     B2_TRY(fork_stream(kv, st, &run));
     B2_TRY(decode_step_run(m, kv, B, run));
@@ -1062,10 +1183,10 @@ int b2_decode_step(b2_model* m, b2_kv* kv, const int32_t* tokens, int B, void* l
     for (int b = 0; b < B; ++b) kv->len_host[b]++;
     if (logits_out)
         B2_CUDA_CHECK(cudaMemcpyAsync(logits_out, m->logits.p, (size_t)B * m->d.vocab * 4, cudaMemcpyDefault, st));
-    if (next_tokens_out) {
+    if (next_tokens_out)
         B2_CUDA_CHECK(cudaMemcpyAsync(next_tokens_out, kv->tok.p, (size_t)B * 4, cudaMemcpyDefault, st));
-        B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    }
+    B2_TRY(ws_leave(m, st));
+    if (next_tokens_out && !is_device_pointer(next_tokens_out)) B2_CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -1083,15 +1204,126 @@ int b2_decode_greedy(b2_model* m, b2_kv* kv, const int32_t* first_tokens, int B,
         B2_CHECK_ARG(kv->len_host[b] >= 1 && kv->len_host[b] + n_steps <= kv->max_seq,
                      "b2_decode_greedy: sample %d cache length %d + %d steps exceeds capacity %d", b, kv->len_host[b],
                      n_steps, kv->max_seq);
+    B2_TRY(ws_enter(m, st));
     B2_TRY(copy_tokens_in(kv, first_tokens, B, st));
     B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
+    B2_TRY(set_greedy_unpublished(kv, st));
     cudaStream_t run = nullptr;
     B2_TRY(fork_stream(kv, st, &run));
     for (int s = 0; s < n_steps; ++s) B2_TRY(decode_step_run(m, kv, B, run));
     B2_TRY(join_stream(kv, st, run));
     for (int b = 0; b < B; ++b) kv->len_host[b] += n_steps;
     B2_CUDA_CHECK(cudaMemcpyAsync(out_tokens, kv->out_tokens.p, (size_t)n_steps * B * 4, cudaMemcpyDefault, st));
-    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    B2_TRY(ws_leave(m, st));
+    // a device destination stays asynchronous on the caller's stream; a host destination must be complete on return
+    if (!is_device_pointer(out_tokens)) B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- streaming decode: the device runs ahead, the host reads tokens from mapped pinned memory ---------------------------
+int b2_stream_begin(b2_model* m, b2_kv* kv, const float* logits, int B, const b2_sampling* sp, void* stream) {
+    B2_CHECK_ARG(m && kv && logits && kv->m == m, "b2_stream_begin: bad handle");
+    B2_CHECK_ARG(m->finalized, "b2_stream_begin: model not finalized");
+    B2_CHECK_ARG(B >= 1 && B <= kv->max_batch, "b2_stream_begin: B=%d exceeds cache batch %d", B, kv->max_batch);
+    SampleState v = {};
+    v.temperature = 1.f; v.top_p = 1.f;
+    if (sp != nullptr && sp->do_sample) {
+        B2_CHECK_ARG(sp->temperature > 0.f, "b2_stream_begin: temperature must be positive when sampling (got %g)", (double)sp->temperature);
+        B2_CHECK_ARG(sp->top_p > 0.f && sp->top_p <= 1.f, "b2_stream_begin: top_p must be in (0, 1] (got %g)", (double)sp->top_p);
+        B2_CHECK_ARG(sp->top_k >= 0, "b2_stream_begin: top_k must be >= 0");
+        v.do_sample = 1; v.temperature = sp->temperature; v.top_p = sp->top_p; v.top_k = sp->top_k; v.seed = sp->seed;
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int b = 0; b < B; ++b)
+        B2_CHECK_ARG(kv->len_host[b] >= 1, "b2_stream_begin: sample %d has an empty cache (prefill first)", b);
+    kv->epoch += 1;
+    v.tag = 1 + kv->epoch % 2047;
+    B2_TRY(ws_enter(m, st));
+    B2_TRY(set_sampling(kv, v, true, st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
+    // token 0: chosen from the prefill's last-position logits, published as ring entry 0, fed to the first decode step
+    B2_TRY(sample_publish(logits, m->d.vocab, B, kv->sstate.as<SampleState>(), kv->tok.as<int32_t>(), nullptr,
+                          kv->step_counter.as<int32_t>(), kv->len_dev.as<int32_t>(), kv->ring_dev, kv->ring_cap, SP_SELECT, 0, st));
+    kv->stream_B = B; kv->stream_tag = v.tag; kv->stream_scheduled = 1;
+    return ws_leave(m, st);
+}
+
+int b2_stream_enqueue(b2_model* m, b2_kv* kv, int n_steps, void* stream) {
+    B2_CHECK_ARG(m && kv && kv->m == m && n_steps >= 1, "b2_stream_enqueue: bad argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    B2_CHECK_ARG(kv->stream_B >= 1, "b2_stream_enqueue: no streaming generation on this cache (b2_stream_begin first)");
+    const int B = kv->stream_B;
+    B2_CHECK_ARG(kv->stream_scheduled + n_steps <= kv->ring_cap, "b2_stream_enqueue: %d tokens exceed the ring capacity %d",
+                 kv->stream_scheduled + n_steps, kv->ring_cap);
+    for (int b = 0; b < B; ++b)
+        B2_CHECK_ARG(kv->len_host[b] + n_steps <= kv->max_seq, "b2_stream_enqueue: sample %d cache length %d + %d steps exceeds capacity %d",
+                     b, kv->len_host[b], n_steps, kv->max_seq);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(ws_enter(m, st));
+    cudaStream_t run = nullptr;
+    B2_TRY(fork_stream(kv, st, &run));
+    for (int s = 0; s < n_steps; ++s) B2_TRY(decode_step_run(m, kv, B, run));
+    B2_TRY(join_stream(kv, st, run));
+    for (int b = 0; b < B; ++b) kv->len_host[b] += n_steps;
+    kv->stream_scheduled += n_steps;
+    return ws_leave(m, st);
+}
+
+// Blocks (the Python binding releases the GIL around it) until token `index` of the current generation is in the ring.
+// Takes no lock: other threads keep issuing work on the model while this one waits.
+int b2_stream_wait(b2_kv* kv, int index, int32_t* tokens_host, int timeout_ms) {
+    B2_CHECK_ARG(kv && tokens_host && index >= 0, "b2_stream_wait: bad argument");
+    const int B = kv->stream_B, tag = kv->stream_tag;
+    B2_CHECK_ARG(B >= 1, "b2_stream_wait: no streaming generation on this cache");
+    B2_CHECK_ARG(index < kv->stream_scheduled, "b2_stream_wait: token %d has not been scheduled (%d scheduled)", index,
+                 kv->stream_scheduled);
+    volatile int32_t* slot = kv->ring_host + (size_t)(index % kv->ring_cap) * B;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned long long spins = 0;; ++spins) {
+        bool ready = true;
+        for (int b = 0; b < B; ++b)
+            if ((slot[b] >> 20) != tag) { ready = false; break; }
+        if (ready) {
+            for (int b = 0; b < B; ++b) tokens_host[b] = slot[b] & 0xFFFFF;
+            return 0;
+        }
+        if (spins < 4096) continue;                 // ~ tens of microseconds of pure polling, then back off
+        struct timespec nap = {0, 20000};
+        nanosleep(&nap, nullptr);
+        if ((spins & 255) == 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+            cudaError_t e = cudaPeekAtLastError();  // a sticky fault (illegal address, trap) would never publish the token
+            if (e != cudaSuccess) { set_error("b2_stream_wait: CUDA error while waiting for token %d: %s", index, cudaGetErrorString(e)); return -2; }
+            if (timeout_ms > 0 && ms > timeout_ms) { set_error("b2_stream_wait: token %d not published after %d ms", index, timeout_ms); return -3; }
+        }
+    }
+}
+
+// standalone selection (unit tests, first-token choice outside a streaming generation): out_tokens[b] (device int32)
+int b2_op_sample(const float* logits, int B, int V, const b2_sampling* sp, int index, int32_t* out_tokens, void* stream) {
+    B2_CHECK_ARG(logits && out_tokens && B >= 1 && V >= 1 && index >= 0, "b2_op_sample: bad argument");
+    SampleState v = {};
+    v.temperature = 1.f; v.top_p = 1.f;
+    if (sp != nullptr && sp->do_sample) {
+        B2_CHECK_ARG(sp->temperature > 0.f && sp->top_p > 0.f && sp->top_p <= 1.f && sp->top_k >= 0, "b2_op_sample: bad sampling parameters");
+        v.do_sample = 1; v.temperature = sp->temperature; v.top_p = sp->top_p; v.top_k = sp->top_k; v.seed = sp->seed;
+    }
+    v.pub_counter = index;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DevBuf tmp;
+    B2_TRY(tmp.alloc(sizeof(SampleState) + 64));
+    int r = sample_state_set(tmp.as<SampleState>(), v, st);
+    if (r == 0)
+        r = sample_publish(logits, V, B, tmp.as<SampleState>(), out_tokens, nullptr, nullptr, nullptr, nullptr, 0, SP_SELECT, 0, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    tmp.free();
+    if (r != 0) return r;
+    B2_CUDA_CHECK(e);
     return 0;
 }
 

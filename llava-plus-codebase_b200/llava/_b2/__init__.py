@@ -36,6 +36,17 @@ class ModelDesc(_c.Structure):
     ]
 
 
+class Sampling(_c.Structure):
+    """b2_sampling (include/b2llava.h): do_sample == 0 -> greedy argmax."""
+    _fields_ = [("do_sample", _c.c_int32), ("temperature", _c.c_float), ("top_p", _c.c_float),
+                ("top_k", _c.c_int32), ("seed", _c.c_ulonglong)]
+
+
+def make_sampling(do_sample=False, temperature=1.0, top_p=1.0, top_k=0, seed=0):
+    return Sampling(int(bool(do_sample)), float(temperature), float(1.0 if top_p is None else top_p),
+                    int(top_k or 0), int(seed) & (2**64 - 1))
+
+
 # name -> (restype, argtypes); must list every symbol include/b2llava.h declares (tests check this)
 SIGNATURES = {
     "b2_init": (_i32, [_i32]),
@@ -54,7 +65,12 @@ SIGNATURES = {
     "b2_vit_encode": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2_project": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2_encode_images": (_i32, [_vp, _vp, _i32, _vp, _vp]),
-    "b2_splice": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "b2_splice": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "b2_async_error": (_i32, [_vp, _c.POINTER(_c.c_int)]),
+    "b2_stream_begin": (_i32, [_vp, _vp, _vp, _i32, _c.POINTER(Sampling), _vp]),
+    "b2_stream_enqueue": (_i32, [_vp, _vp, _i32, _vp]),
+    "b2_stream_wait": (_i32, [_vp, _i32, _c.POINTER(_c.c_int32), _i32]),
+    "b2_op_sample": (_i32, [_vp, _i32, _i32, _c.POINTER(Sampling), _i32, _vp, _vp]),
     "b2_prefill": (_i32, [_vp, _vp, _vp, _c.POINTER(_c.c_int32), _i32, _i32, _vp, _i32, _vp]),
     "b2_decode_step": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b2_decode_greedy": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
@@ -253,12 +269,22 @@ class Engine:
         return out
 
     def splice(self, src_index, image_feats, B, S):
-        """src_index: int32 device tensor [B*S]; image_feats: bf16 [n_rows, hidden] or None."""
+        """src_index: int32 device tensor [B*S]; image_feats: bf16 [n_rows, hidden] or None. Ids / rows out of range
+        become zero rows and are reported by check_async_error() (never an out-of-bounds read)."""
         out = torch.empty(B, S, self.hidden, dtype=torch.bfloat16, device=self.device)
+        n_rows = 0 if image_feats is None else int(image_feats.shape[0])
         with torch.cuda.device(self.index):
-            check(self.lib.b2_splice(self.handle, ptr(src_index), ptr(image_feats), B * S, ptr(out), stream_ptr()),
+            check(self.lib.b2_splice(self.handle, ptr(src_index), ptr(image_feats), n_rows, B * S, ptr(out), stream_ptr()),
                   "b2_splice")
         return out
+
+    def check_async_error(self):
+        """Raise ValueError if a kernel flagged bad inputs (ids outside the embedding table, image placeholder without
+        features). Call after a point where the stream has been synchronised (e.g. once the first token is on the host)."""
+        code = _c.c_int(0)
+        check(self.lib.b2_async_error(self.handle, ctypes.byref(code)), "b2_async_error")
+        if code.value:
+            raise ValueError(last_error())
 
     def prefill(self, kv, embeds, seq_lens=None, logits_mode=LOGITS_LAST):
         embeds = self._bf16(embeds)
@@ -296,6 +322,35 @@ class Engine:
         with torch.cuda.device(self.index):
             check(self.lib.b2_decode_greedy(self.handle, kv.handle, ptr(first_tokens), B, int(n_steps), ptr(out),
                                             stream_ptr()), "b2_decode_greedy")
+        return out
+
+    # -- streaming decode (device runs ahead, host reads tokens from mapped pinned memory) ---------------
+    def stream_begin(self, kv, logits, sampling=None):
+        """Token 0 is chosen from the prefill logits [B, vocab] on the device and published as ring index 0."""
+        logits = logits.contiguous()
+        sp = sampling if sampling is not None else make_sampling()
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_stream_begin(self.handle, kv.handle, ptr(logits), int(logits.shape[0]), ctypes.byref(sp),
+                                           stream_ptr()), "b2_stream_begin")
+
+    def stream_enqueue(self, kv, n_steps):
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_stream_enqueue(self.handle, kv.handle, int(n_steps), stream_ptr()), "b2_stream_enqueue")
+
+    def stream_wait(self, kv, index, B, timeout_ms=60000):
+        """Blocks (GIL released by ctypes) until token `index` is visible; returns a list of B ints."""
+        out = (_c.c_int32 * B)()
+        check(self.lib.b2_stream_wait(kv.handle, int(index), out, int(timeout_ms)), "b2_stream_wait")
+        return list(out)
+
+    def sample(self, logits, sampling, index=0):
+        """One selection per row of fp32 logits [B, V] with csrc/sampling.cu (greedy or temperature/top-k/top-p)."""
+        logits = logits.to(device=self.device, dtype=torch.float32).contiguous()
+        B, V = logits.shape
+        out = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_op_sample(ptr(logits), B, V, ctypes.byref(sampling), int(index), ptr(out), stream_ptr()),
+                  "b2_op_sample")
         return out
 
     def argmax(self, logits):

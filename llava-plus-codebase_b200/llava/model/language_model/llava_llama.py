@@ -13,6 +13,7 @@ reference's builder.py:43) keep their tensor dtypes at the boundary, the engine 
 """
 import json
 import os
+import threading
 import weakref
 from typing import List, Optional, Tuple, Union
 
@@ -23,11 +24,59 @@ from transformers.modeling_outputs import CausalLMOutputWithPast
 
 from ..llava_arch import LlavaMetaModel, LlavaMetaForCausalLM
 from ..multimodal_encoder.clip_encoder import _Holder, _read_checkpoint_dir
-from ..._b2 import Engine, KVCache, LOGITS_ALL, LOGITS_LAST
+from ..._b2 import Engine, KVCache, LOGITS_ALL, LOGITS_LAST, make_sampling
 
 
 class LlavaConfig(LlamaConfig):
     model_type = "llava"
+
+
+class _KVPool:
+    """KV caches of one engine. Every generate() works on a cache of its own for its whole duration — the reference's
+    model_worker runs up to `limit_model_concurrency` generate() threads on one model object
+    (llava/serve/model_worker.py:174-185, :230-243), and a shared cache would let request B's prefill overwrite request
+    A's context mid-decode. Caches are created on demand (up to `cap`, then acquire() blocks) and reused."""
+
+    def __init__(self, engine, max_batch, max_seq, cap):
+        self.engine, self.max_batch, self.max_seq, self.cap = engine, max_batch, max_seq, max(1, int(cap))
+        self._cond = threading.Condition()
+        self._free, self._made = [], 0
+
+    def acquire(self):
+        with self._cond:
+            while not self._free and self._made >= self.cap:
+                self._cond.wait()
+            if self._free:
+                return self._free.pop()
+            self._made += 1
+        try:
+            return self.engine.new_kv(self.max_batch, self.max_seq)
+        except Exception:
+            with self._cond:
+                self._made -= 1
+                self._cond.notify()
+            raise
+
+    def release(self, kv):
+        with self._cond:
+            self._free.append(kv)
+            self._cond.notify()
+
+
+class PastKeyValues:
+    """What forward(use_cache=True) returns as `past_key_values`: a lease on one of the model's forward caches. A later
+    forward() may recycle the underlying cache (`config.b2_forward_caches` of them exist, default 2); using a recycled
+    lease raises instead of silently decoding against somebody else's context."""
+
+    def __init__(self, kv, serial):
+        self.kv, self.serial = kv, serial
+
+    @property
+    def valid(self):
+        return getattr(self.kv, "_lease_serial", None) == self.serial
+
+    def get_seq_length(self, layer_idx=0):
+        return self.kv.get_seq_length()
 
 
 def _empty_param(*shape, dtype=None, device=None):
@@ -94,7 +143,10 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         self.vocab_size = config.vocab_size
         self.lm_head = _Weight(config.vocab_size, config.hidden_size, dtype=dtype, device=device)
         self._engine = None
-        self._kv = None
+        self._pool = None          # generate(): one exclusive cache per call
+        self._fwd_kvs = []         # forward(use_cache=True): small LRU ring of leased caches
+        self._fwd_lock = threading.Lock()
+        self._engine_lock = threading.RLock()
         self._limits = {"max_batch": max_batch, "max_seq": max_seq, "max_images": max_images}
         self._attach()
 
@@ -127,10 +179,12 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
 
     def invalidate_engine(self):
         """Weights changed (load_state_dict, resize, tower load): rebuild the device engine lazily."""
-        self._kv = None
-        if self._engine is not None:
-            self._engine.close()
-        self._engine = None
+        with self._engine_lock:
+            self._pool = None
+            self._fwd_kvs = []
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = None
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         r = super().load_state_dict(state_dict, strict=strict, assign=assign)
@@ -166,6 +220,13 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
                 self.invalidate_engine()
 
     def _ensure_engine(self) -> Engine:
+        eng = self._engine
+        if eng is not None:
+            return eng
+        with self._engine_lock:
+            return self._build_engine()
+
+    def _build_engine(self) -> Engine:
         if self._engine is not None:
             return self._engine
         vt = self.get_vision_tower()
@@ -188,7 +249,8 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         if getattr(vc, "hidden_act", "quick_gelu") != "quick_gelu":
             raise NotImplementedError("CLIP tower activation must be quick_gelu (openai/clip-vit-large-patch14-336)")
         eng = Engine(desc, self.device)
-        for k, v in self.state_dict().items():
+        torch.cuda.current_stream(self.device).synchronize()  # set_weight copies on the library's stream: order it after
+        for k, v in self.state_dict().items():                # whatever produced the parameters on the caller's stream
             if "position_ids" in k or "inv_freq" in k:
                 continue
             eng.set_weight(k, v.to(self.device))
@@ -196,19 +258,31 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         # BASELINE configs[4] opt-in: e4m3 decoder weights for batch >= 7 decode (config.b2_fp8_decode or B2_FP8_DECODE=1)
         if getattr(c, "b2_fp8_decode", False) or os.environ.get("B2_FP8_DECODE") == "1":
             eng.enable_fp8_decode()
+        self._pool = _KVPool(eng, desc["max_batch"], desc["max_seq"],
+                             getattr(c, "b2_max_concurrent_generations", None) or int(os.environ.get("B2_MAX_GENERATIONS", "8")))
+        self._fwd_kvs = []
         self._engine = eng
-        self._kv = None
         return eng
 
-    def _get_kv(self, B, need_seq):
-        eng = self._ensure_engine()
+    def _check_limits(self, eng, B, need_seq):
         lim_b, lim_s = eng.desc.max_batch, eng.desc.max_seq
         if B > lim_b or need_seq > lim_s:
             raise ValueError(f"batch {B} / sequence {need_seq} exceed the engine limits (max_batch={lim_b}, max_seq={lim_s}); "
                              f"call model.engine_limits(max_batch=..., max_seq=...) before the first forward")
-        if self._kv is None:
-            self._kv = eng.new_kv(lim_b, lim_s)
-        return self._kv
+
+    def _lease_forward_kv(self, eng, B, need_seq):
+        """Cache for one forward(use_cache=True): least recently leased of a small ring; earlier leases of it go stale."""
+        self._check_limits(eng, B, need_seq)
+        with self._fwd_lock:
+            cap = max(1, int(getattr(self.config, "b2_forward_caches", 2)))
+            if len(self._fwd_kvs) < cap:
+                kv = eng.new_kv(eng.desc.max_batch, eng.desc.max_seq)
+                kv._lease_serial = 0
+            else:
+                kv = self._fwd_kvs.pop(0)
+            kv._lease_serial += 1
+            self._fwd_kvs.append(kv)
+            return PastKeyValues(kv, kv._lease_serial)
 
     # ------------------------------------------------------------------ forward (ref llava_llama.py:56-99)
     def forward(
@@ -231,9 +305,16 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
 
         # ---- decode step: [B,1] ids against an engine cache ----
         if inputs_embeds is None and past_key_values is not None and input_ids is not None and input_ids.shape[1] == 1:
-            if not isinstance(past_key_values, KVCache):
+            if isinstance(past_key_values, PastKeyValues):
+                if not past_key_values.valid:
+                    raise RuntimeError("this past_key_values was recycled by a later forward(use_cache=True): the model keeps "
+                                       "config.b2_forward_caches (default 2) forward caches alive at a time")
+                kv = past_key_values.kv
+            elif isinstance(past_key_values, KVCache):
+                kv = past_key_values
+            else:
                 raise ValueError("past_key_values must be the cache object returned by a previous forward of this model")
-            logits = engine.decode_step(past_key_values, input_ids.reshape(-1))
+            logits = engine.decode_step(kv, input_ids.reshape(-1))
             logits = logits.unsqueeze(1)
             return self._output(logits, past_key_values, labels, return_dict)
 
@@ -254,12 +335,12 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             left = bool((~m[:, 0]).any()) and bool(m[:, -1].all())
             if left:  # engine rows are right-padded: rotate valid tokens to the front (ref pads left only on request)
                 inputs_embeds = torch.stack([torch.roll(inputs_embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
-        kv = self._get_kv(B, S)
-        kv.reset()
-        logits = engine.prefill(kv, inputs_embeds, lens, LOGITS_ALL)
+        lease = self._lease_forward_kv(engine, B, S)
+        lease.kv.reset()
+        logits = engine.prefill(lease.kv, inputs_embeds, lens, LOGITS_ALL)
         if left:
             logits = torch.stack([torch.roll(logits[b], shifts=(S - lens[b]), dims=0) for b in range(B)])
-        return self._output(logits, kv if use_cache is not False else None, labels, return_dict)
+        return self._output(logits, lease if use_cache is not False else None, labels, return_dict)
 
     def _output(self, logits, kv, labels, return_dict):
         loss = None
@@ -286,15 +367,33 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         return model_inputs
 
     # ------------------------------------------------------------------ generate
+    # generation arguments of HF generate() that change WHAT is generated and that this loop does not implement: raise
+    # instead of silently decoding something else (value = the setting that means "off")
+    _UNSUPPORTED_GENERATION_ARGS = {
+        "repetition_penalty": 1.0, "encoder_repetition_penalty": 1.0, "length_penalty": 1.0, "no_repeat_ngram_size": 0,
+        "encoder_no_repeat_ngram_size": 0, "min_new_tokens": None, "min_length": 0, "bad_words_ids": None,
+        "force_words_ids": None, "num_beam_groups": 1, "diversity_penalty": 0.0, "penalty_alpha": None, "typical_p": 1.0,
+        "epsilon_cutoff": 0.0, "eta_cutoff": 0.0, "num_return_sequences": 1, "logits_processor": None,
+        "prefix_allowed_tokens_fn": None, "constraints": None, "suppress_tokens": None, "begin_suppress_tokens": None,
+        "forced_bos_token_id": None, "forced_eos_token_id": None, "assistant_model": None, "min_p": None,
+    }
+    # accepted and without effect on this path
+    _IGNORED_GENERATION_ARGS = {"synced_gpus", "early_stopping", "output_attentions", "output_hidden_states",
+                                "generation_config", "position_ids", "past_key_values", "renormalize_logits", "max_time"}
+
     @torch.no_grad()
     def generate(self, inputs=None, images=None, do_sample=False, temperature=1.0, top_p=None, top_k=None,
                  num_beams=1, max_new_tokens=None, max_length=None, use_cache=True, streamer=None,
                  stopping_criteria=None, eos_token_id=None, pad_token_id=None, attention_mask=None,
                  input_ids=None, output_scores=False, return_dict_in_generate=False, **kwargs):
-        """Own decoding loop with the side-protocols the reference's callers rely on:
-        prompt ids (with IMAGE_TOKEN_INDEX) echoed in the result, `streamer.put/end`, `stopping_criteria`
-        called as crit(ids_so_far, scores) -> bool | bool tensor, eos stop, temperature/top-p sampling.
-        Pure greedy runs without criteria/streamer stay on the device for the whole loop (CUDA-graph replay)."""
+        """Own decoding loop with the side-protocols the reference's callers rely on: prompt ids (with
+        IMAGE_TOKEN_INDEX) echoed in the result, `streamer.put/end`, `stopping_criteria` called as
+        crit(ids_so_far, scores) -> bool | bool tensor, eos stop, temperature / top-k / top-p sampling.
+
+        Every variant runs the same device-resident loop: token feedback, argmax or the sampling draw are kernels, each
+        step publishes its token into pinned host memory, and this thread (usually a worker `Thread`,
+        llava/serve/model_worker.py:174-185) reads token t — streamer, eos, stopping criteria — while the device is
+        already `config.b2_run_ahead` (default 8) steps further. Steps queued beyond the stop point are discarded."""
         if inputs is None:
             inputs = input_ids
         if inputs is None:
@@ -303,6 +402,14 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             raise NotImplementedError("beam search is not used on the LLaVA path (num_beams=1 everywhere)")
         if return_dict_in_generate or output_scores:
             raise NotImplementedError("generate() returns the id tensor only")
+        for k, v in kwargs.items():
+            if k in self._IGNORED_GENERATION_ARGS:
+                continue
+            if k in self._UNSUPPORTED_GENERATION_ARGS:
+                if v is None or v == self._UNSUPPORTED_GENERATION_ARGS[k]:
+                    continue
+                raise NotImplementedError(f"generate({k}={v!r}) is not implemented on the B200 path")
+            raise NotImplementedError(f"generate() got an unsupported argument {k!r}")
         prompt = inputs if inputs.dim() == 2 else inputs.unsqueeze(0)
         B, Lt = prompt.shape
         engine = self._ensure_engine()
@@ -314,68 +421,53 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         if max_new_tokens <= 0:
             raise ValueError("max_new_tokens must be positive")
         greedy = (not do_sample) or (temperature is not None and temperature <= 1e-5)
+        if greedy:
+            sampling = make_sampling()
+        else:
+            if top_p is not None and not (0.0 < top_p <= 1.0):
+                raise ValueError(f"top_p must be in (0, 1], got {top_p}")
+            # HF GenerationConfig defaults: top_k = 50, top_p = 1.0; the draw is seeded from torch's CPU generator so that
+            # torch.manual_seed() makes a run repeatable
+            seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+            sampling = make_sampling(True, temperature, 1.0 if top_p is None else top_p, 50 if top_k is None else top_k, seed)
         prof = _StageTimer() if os.environ.get("B2_PROFILE_GENERATE") else None
 
-        # ---- prefill: splice + decoder, last-position logits only ----
-        if images is not None and self.get_vision_tower() is not None:
-            _, _, _, _, embeds, _ = self.prepare_inputs_labels_for_multimodal(prompt, None, attention_mask, None, None, images)
-            lens = self._last_splice_lens
-            if getattr(self.config, "tokenizer_padding_side", "right") == "left" and len(set(lens)) > 1:
-                S = embeds.shape[1]
-                embeds = torch.stack([torch.roll(embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
-        else:
-            if attention_mask is not None and not bool(attention_mask.bool().all()):
-                raise NotImplementedError("padded text-only batches: pass equal-length prompts")
-            ids = prompt.to(torch.int32).reshape(-1).to(engine.device)
-            embeds = engine.splice(ids, None, B, Lt)
-            lens = [Lt] * B
-        S = embeds.shape[1]
-        if prof: prof.mark("encode_images+splice")
-        kv = self._get_kv(B, max(lens) + max_new_tokens)
-        kv.reset()
-        logits = engine.prefill(kv, embeds, lens, LOGITS_LAST)
-        if prof: prof.mark("prefill")
+        kv = self._pool.acquire()  # exclusive for this call (concurrent generate() threads each get their own)
+        try:
+            # ---- prefill: splice + decoder, last-position logits only ----
+            embeds = None
+            if images is not None and self.get_vision_tower() is not None:
+                embeds, lens = self._spliced_embeds(prompt, attention_mask, images)
+            if embeds is not None:
+                if getattr(self.config, "tokenizer_padding_side", "right") == "left" and len(set(lens)) > 1:
+                    S = embeds.shape[1]
+                    embeds = torch.stack([torch.roll(embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
+            else:  # text-only prompt (or a [B,1] prompt, which the multimodal splice passes through)
+                if attention_mask is not None and not bool(attention_mask.bool().all()):
+                    raise NotImplementedError("padded text-only batches: pass equal-length prompts")
+                ids = prompt.to(torch.int32).reshape(-1).to(engine.device)
+                embeds = engine.splice(ids, None, B, Lt)
+                lens = [Lt] * B
+            if prof: prof.mark("encode_images+splice")
+            self._check_limits(engine, B, max(lens) + max_new_tokens)
+            kv.reset()
+            logits = engine.prefill(kv, embeds, lens, LOGITS_LAST)
+            if prof: prof.mark("prefill")
 
-        if streamer is not None:
-            streamer.put(prompt.cpu())
-
-        pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
-        if greedy and streamer is None and not stopping_criteria:
-            # nobody observes individual steps: the loop stays on the device (one megakernel launch / graph replay per
-            # token, no host round trip) in chunks; eos is checked once per chunk on the host
-            first = engine.argmax(logits)
-            new_tokens = _greedy_chunked(engine, kv, first, max_new_tokens, eos_ids, pad)
-            if prof: prof.mark("decode_greedy")
-            out = torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
-            if prof: prof.mark("ids to host"); prof.report()
-            return out
-
-        out = prompt.clone()
-        finished = torch.zeros(B, dtype=torch.bool)
-        for step in range(max_new_tokens):
-            if greedy:
-                nxt = engine.argmax(logits)
-            else:
-                nxt = _sample(logits, temperature, top_p, top_k)
-            nxt_cpu = nxt.to("cpu", torch.long)
-            nxt_cpu = torch.where(finished, torch.full_like(nxt_cpu, pad), nxt_cpu)
-            out = torch.cat([out, nxt_cpu.to(out.device, out.dtype).unsqueeze(1)], dim=1)
             if streamer is not None:
-                streamer.put(nxt_cpu)
-            for b in range(B):
-                if int(nxt_cpu[b]) in eos_ids:
-                    finished[b] = True
-            stop = bool(finished.all())
-            if stopping_criteria:
-                for crit in stopping_criteria:
-                    r = crit(out, None)
-                    r = bool(r.all()) if torch.is_tensor(r) else bool(r)
-                    stop = stop or r
-            if stop or step == max_new_tokens - 1:
-                break
-            logits = engine.decode_step(kv, nxt_cpu.to(torch.int32))
+                streamer.put(prompt.cpu())
+            pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
+            new_tokens = _stream_decode(engine, kv, logits, sampling, B, max_new_tokens, eos_ids, pad, prompt,
+                                        streamer, stopping_criteria,
+                                        run_ahead=int(getattr(self.config, "b2_run_ahead", 8)))
+            engine.check_async_error()  # the first token has been read: every input check of this call has run
+            if prof: prof.mark("decode")
+        finally:
+            self._pool.release(kv)
         if streamer is not None:
             streamer.end()
+        out = torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
+        if prof: prof.mark("ids to caller"); prof.report()
         return out
 
     # ------------------------------------------------------------------ checkpoints
@@ -413,39 +505,48 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         return super().eval()
 
 
-def _greedy_chunked(engine, kv, first, max_new_tokens, eos_ids, pad, chunk=16):
-    """Greedy decoding without per-step observers, equivalent to the per-step loop in generate(): `first` (int32 device
-    tensor [B]) is the token chosen from the prefill logits; further tokens come from engine.decode_greedy in chunks of
-    `chunk` steps (device-resident token feedback). After every chunk the host scans for eos: a finished row shows `pad`
-    from then on, generation stops at the step where every row has finished (the device may have run up to chunk-1 steps
-    past it; they are discarded — rows of a batch never interact, so unfinished rows are unaffected by what finished rows
-    were fed). With no eos ids this is a single chunk. Returns a CPU int64 tensor [B, n], 1 <= n <= max_new_tokens."""
-    B = int(first.numel())
-    finished = torch.zeros(B, dtype=torch.bool)
+def _stream_decode(engine, kv, logits, sampling, B, max_new_tokens, eos_ids, pad, prompt, streamer, stopping_criteria,
+                   run_ahead=8):
+    """Host half of the decode loop. The device chooses token 0 from the prefill `logits` and then runs up to `run_ahead`
+    steps in front of this loop; `engine.stream_wait(kv, t, B)` hands over token t as soon as its kernel has written it
+    to pinned memory. Per token, in the order HF's loop uses: finished rows show `pad`; streamer.put; eos bookkeeping;
+    stopping criteria on cat(prompt, tokens so far) (the reference's KeywordsStoppingCriteria looks at the tail of that
+    tensor, llava/mm_utils.py:92-114). Returns a CPU int64 tensor [B, n], 1 <= n <= max_new_tokens."""
+    Lt = prompt.shape[1]
+    crit_buf = None
+    if stopping_criteria:
+        crit_buf = torch.empty(B, Lt + max_new_tokens, dtype=torch.long)
+        crit_buf[:, :Lt] = prompt.to("cpu", torch.long)
+    run_ahead = max(1, int(run_ahead))
+    engine.stream_begin(kv, logits, sampling)
+    scheduled = 1                                   # tokens whose kernels have been queued (token 0 = begin)
+    finished = [False] * B
     cols = []
-
-    def push(col):
-        col = torch.where(finished, torch.full_like(col, pad), col)
+    for t in range(max_new_tokens):
+        # keep the device `run_ahead` tokens in front of the host (queued in blocks: one call per ~run_ahead/2 tokens)
+        if scheduled < max_new_tokens and scheduled - t <= (run_ahead + 1) // 2:
+            n = min(run_ahead - (scheduled - t) + 1, max_new_tokens - scheduled)
+            if n > 0:
+                engine.stream_enqueue(kv, n)
+                scheduled += n
+        toks = engine.stream_wait(kv, t, B)
+        col = [pad if finished[b] else int(toks[b]) for b in range(B)]
         cols.append(col)
+        if streamer is not None:
+            streamer.put(torch.tensor(col, dtype=torch.long))
         for b in range(B):
-            if int(col[b]) in eos_ids:
+            if col[b] in eos_ids:
                 finished[b] = True
-        return bool(eos_ids) and bool(finished.all())
-
-    stop = push(first.to("cpu", torch.long))
-    done, last = 1, first
-    step = chunk if eos_ids else max_new_tokens
-    while not stop and done < max_new_tokens:
-        n = min(step, max_new_tokens - done)
-        rest = engine.decode_greedy(kv, last, n)          # [n, B] on the device
-        rest_cpu = rest.to("cpu", torch.long)
-        for i in range(n):
-            done += 1
-            if push(rest_cpu[i]):
-                stop = True
-                break
-        last = rest[n - 1]
-    return torch.stack(cols, dim=1)
+        stop = bool(eos_ids) and all(finished)
+        if crit_buf is not None:
+            crit_buf[:, Lt + t] = torch.tensor(col, dtype=torch.long)
+            view = crit_buf[:, :Lt + t + 1]
+            for crit in stopping_criteria:
+                r = crit(view, None)
+                stop = stop or (bool(r.all()) if torch.is_tensor(r) else bool(r))
+        if stop:
+            break
+    return torch.tensor(cols, dtype=torch.long).t().contiguous()
 
 
 class _StageTimer:
@@ -465,21 +566,6 @@ class _StageTimer:
     def report(self):
         import sys
         print("generate stages (ms): " + ", ".join(f"{n} {ms:.2f}" for n, ms in self._rows), file=sys.stderr)
-
-
-def _sample(logits, temperature, top_p, top_k):
-    """temperature / top-k / top-p sampling on last-position logits (HF LogitsWarper semantics)."""
-    x = logits.float() / max(float(temperature), 1e-5)
-    if top_k:
-        kth = torch.topk(x, int(top_k), dim=-1).values[..., -1, None]
-        x = x.masked_fill(x < kth, float("-inf"))
-    if top_p is not None and top_p < 1.0:
-        sorted_x, idx = torch.sort(x, descending=False, dim=-1)
-        cum = sorted_x.softmax(dim=-1).cumsum(dim=-1)
-        remove = cum <= (1 - top_p)
-        remove[..., -1:] = False
-        x = x.masked_fill(remove.scatter(-1, idx, remove), float("-inf"))
-    return torch.multinomial(x.softmax(dim=-1), 1).squeeze(-1).to(torch.int32)
 
 
 try:  # the installed transformers may already ship a "llava" model type (ref llava_llama.py:110-111)

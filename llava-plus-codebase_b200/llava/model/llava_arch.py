@@ -36,34 +36,29 @@ class LlavaMetaModel:
         return vision_tower
 
     def initialize_vision_modules(self, model_args, fsdp=None):
-        """ref llava_arch.py:42-82 (config bookkeeping + projector weight load)."""
-        vision_tower = model_args.vision_tower
-        mm_vision_select_layer = model_args.mm_vision_select_layer
-        mm_vision_select_feature = model_args.mm_vision_select_feature
-        pretrain_mm_mlp_adapter = getattr(model_args, "pretrain_mm_mlp_adapter", None)
-
-        self.config.mm_vision_tower = vision_tower
-        if self.get_vision_tower() is None:
-            vision_tower = build_vision_tower(model_args)
-            if fsdp is not None and len(fsdp) > 0:
-                self.vision_tower = [vision_tower]
-            else:
-                self.vision_tower = vision_tower
+        """Entry point of the reference's training script (ref llava_arch.py:42-82), kept because callers of the class
+        surface may use it to attach a tower to a bare language model: make sure a loaded tower and a projector exist and
+        record the multimodal settings in the config. Training-only details (FSDP list wrapping aside) are not reproduced."""
+        wrap = fsdp is not None and len(fsdp) > 0
+        tower = self.get_vision_tower()
+        if tower is None:
+            tower = build_vision_tower(model_args)
+            self.vision_tower = [tower] if wrap else tower
         else:
-            vision_tower = self.vision_tower[0] if (fsdp is not None and len(fsdp) > 0) else self.vision_tower
-            vision_tower.load_model()
-
-        self.config.use_mm_proj = True
-        self.config.mm_projector_type = getattr(model_args, "mm_projector_type", "linear")
-        self.config.mm_hidden_size = vision_tower.hidden_size
-        self.config.mm_vision_select_layer = mm_vision_select_layer
-        self.config.mm_vision_select_feature = mm_vision_select_feature
-
+            tower.load_model()
+        cfg = self.config
+        cfg.mm_vision_tower = model_args.vision_tower
+        cfg.use_mm_proj = True
+        cfg.mm_projector_type = getattr(model_args, "mm_projector_type", "linear")
+        cfg.mm_hidden_size = tower.hidden_size
+        cfg.mm_vision_select_layer = model_args.mm_vision_select_layer
+        cfg.mm_vision_select_feature = model_args.mm_vision_select_feature
         if getattr(self, "mm_projector", None) is None:
-            self.mm_projector = build_vision_projector(self.config)
-        if pretrain_mm_mlp_adapter is not None:
-            w = torch.load(pretrain_mm_mlp_adapter, map_location="cpu")
-            self.mm_projector.load_state_dict({k.split("mm_projector.")[1]: v for k, v in w.items() if "mm_projector" in k})
+            self.mm_projector = build_vision_projector(cfg)
+        adapter = getattr(model_args, "pretrain_mm_mlp_adapter", None)
+        if adapter is not None:
+            state = torch.load(adapter, map_location="cpu")
+            self.mm_projector.load_state_dict({k.split("mm_projector.", 1)[1]: v for k, v in state.items() if "mm_projector" in k})
         self._engine_dirty()
 
     def _engine_dirty(self):
@@ -72,15 +67,23 @@ class LlavaMetaModel:
             owner().invalidate_engine()
 
 
-def build_source_index(input_ids, attention_mask, labels, num_image_rows, feats_per_image, max_length, padding_side):
+def build_source_index(input_ids, attention_mask, labels, num_image_rows, feats_per_image, max_length, padding_side,
+                       vocab_size=None):
     """Host half of the splice (ref llava_arch.py:143-225), pure numpy.
 
     input_ids [B, Lt] int64 numpy (IMAGE_TOKEN_INDEX marks an image), attention_mask bool [B, Lt],
     labels int64 [B, Lt]; feats_per_image: list with the number of feature rows of each image slot (global,
-    row-major order, ref :149-179). Returns (src_index int32 [B,S], new_labels int64 [B,S], mask bool [B,S],
+    row-major order, ref :149-179). With `vocab_size`, ids outside the embedding table raise ValueError here instead of
+    reaching the gather kernel. Returns (src_index int32 [B,S], new_labels int64 [B,S], mask bool [B,S],
     position_ids int64 [B,S], lens list[int]).
     """
     B = input_ids.shape[0]
+    if vocab_size is not None:
+        bad = ((input_ids >= vocab_size) | ((input_ids < 0) & (input_ids != IMAGE_TOKEN_INDEX))) & attention_mask
+        if bad.any():
+            b, i = np.argwhere(bad)[0]
+            raise ValueError(f"input_ids[{b}, {i}] = {int(input_ids[b, i])} is outside the embedding table [0, {vocab_size}) "
+                             f"(and is not IMAGE_TOKEN_INDEX = {IMAGE_TOKEN_INDEX})")
     rows_src, rows_lab = [], []
     cur_image_idx = 0
     feat_offset = np.concatenate([[0], np.cumsum(feats_per_image)]).astype(np.int64)
@@ -159,6 +162,17 @@ class LlavaMetaForCausalLM(ABC):
         return feats.reshape(-1, feats.shape[-1]), [P] * feats.shape[0]
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images):
+        return self._prepare_multimodal(input_ids, position_ids, attention_mask, past_key_values, labels, images)[0]
+
+    def _spliced_embeds(self, input_ids, attention_mask, images):
+        """generate()'s use of the splice: (inputs_embeds [B,S,h], valid length per row), or (None, None) when the
+        multimodal branch passes the ids through (single-token prompts)."""
+        out, lens = self._prepare_multimodal(input_ids, None, attention_mask, None, None, images)
+        return out[4], lens
+
+    def _prepare_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images):
+        """The reference's 6-tuple plus the per-row valid lengths of the spliced sequence (no state is kept on `self`:
+        concurrent calls from several threads must not see each other's lengths)."""
         vision_tower = self.get_vision_tower()
         if vision_tower is None or images is None or input_ids.shape[1] == 1:
             # decode branch (ref :103-112): the engine keeps the cache length itself, so only the mask/position
@@ -170,7 +184,7 @@ class LlavaMetaForCausalLM(ABC):
                         (attention_mask.shape[0], target_shape - attention_mask.shape[1]),
                         dtype=attention_mask.dtype, device=attention_mask.device)), dim=1)
                     position_ids = torch.sum(attention_mask, dim=1).unsqueeze(-1) - 1
-            return input_ids, position_ids, attention_mask, past_key_values, None, labels
+            return (input_ids, position_ids, attention_mask, past_key_values, None, labels), None
 
         image_feats, feats_per_image = self._image_features(images)
 
@@ -185,18 +199,18 @@ class LlavaMetaForCausalLM(ABC):
         src, new_labels, mask, pos, lens = build_source_index(
             ids_np, mask_np, lab_np, image_feats.shape[0], feats_per_image,
             getattr(self.config, "tokenizer_model_max_length", None),
-            getattr(self.config, "tokenizer_padding_side", "right"))
+            getattr(self.config, "tokenizer_padding_side", "right"),
+            vocab_size=self.get_model().embed_tokens.weight.shape[0])
         B, S = src.shape
         engine = self._ensure_engine()
         src_dev = torch.from_numpy(src.reshape(-1)).to(engine.device, non_blocking=True)
         new_input_embeds = engine.splice(src_dev, image_feats, B, S)
-        self._last_splice_lens = lens
 
         dev = input_ids.device
         new_labels_t = None if _labels is None else torch.from_numpy(new_labels).to(device=dev, dtype=_labels.dtype)
         attention_mask_t = None if _attention_mask is None else torch.from_numpy(mask).to(device=dev, dtype=_attention_mask.dtype)
         position_ids_t = None if _position_ids is None else torch.from_numpy(pos).to(device=dev, dtype=_position_ids.dtype)
-        return None, position_ids_t, attention_mask_t, past_key_values, new_input_embeds, new_labels_t
+        return (None, position_ids_t, attention_mask_t, past_key_values, new_input_embeds, new_labels_t), lens
 
     def initialize_vision_tokenizer(self, model_args, tokenizer):
         """Token bookkeeping for the optional <im_patch>/<im_start>/<im_end> tokens (ref llava_arch.py:242-284).

@@ -21,6 +21,9 @@ SHAPES = [  # (name, M, N, K, act)
     ("ViT b16 out", 9232, 1024, 1024, 0), ("square 8192", 8192, 8192, 8192, 0),
     ("13B prefill gate/up", 704, 27648, 5120, 3), ("13B prefill o", 704, 5120, 5120, 0),
     ("projector fc1 b1", 576, 4096, 1024, 2), ("projector fc2 b1", 576, 4096, 4096, 0),
+    ("ViT b64 qkv", 36928, 3072, 1024, 0), ("ViT b64 fc1", 36928, 4096, 1024, 1), ("ViT b64 fc2", 36928, 1024, 4096, 0),
+    ("7B prefill b8 qkv", 5632, 12288, 4096, 0), ("7B prefill b8 gate/up swiglu", 5632, 22016, 4096, 3),
+    ("7B prefill b8 down", 5632, 4096, 11008, 0),
 ]
 res = []
 for name, M, N, K, act in SHAPES:
@@ -30,8 +33,8 @@ for name, M, N, K, act in SHAPES:
     bias = torch.zeros(N, device=dev, dtype=torch.bfloat16) if act == 1 else None
     out = torch.empty(M, N // 2 if act == 3 else N, device=dev, dtype=torch.bfloat16)
     row = {"shape": name, "M": M, "N": N, "K": K}
-    for bn in (64, 128, 192, 256):
-        if act == 3 and bn % 128 != 0:
+    for bn in (64, 128, 192, 256, 2):  # 2 = CTA-pair kernel (cta_group::2, 256x256 pair tiles)
+        if act == 3 and bn % 128 != 0 and bn != 2:
             continue
         def run(i):
             W = Ws[i % ncopy]

@@ -66,3 +66,40 @@ def test_entry_point_signatures_match_the_reference():
         _ref_signature(R + "/llava_arch.py", "encode_images", "LlavaMetaForCausalLM")
     assert list(inspect.signature(build_vision_tower).parameters)[0] == _ref_signature(R + "/multimodal_encoder/builder.py", "build_vision_tower")[0]
     assert list(inspect.signature(build_vision_projector).parameters)[:2] == _ref_signature(R + "/multimodal_projector/builder.py", "build_vision_projector")[:2]
+
+
+def test_reference_keywords_stopping_criteria_through_the_decode_loop():
+    """The reference's OWN KeywordsStoppingCriteria (llava/mm_utils.py:79-114, loaded from the reference tree, unmodified)
+    driving generate()'s host loop: it must see cat(prompt ids incl. IMAGE_TOKEN_INDEX, new tokens), one column more per
+    step, and stop the loop at the step whose tail spells the keyword (GPU counterpart with a restated criterion:
+    tests/test_generate_gpu.py)."""
+    import importlib.util
+
+    import torch
+
+    from llava.model.language_model.llava_llama import _stream_decode
+    from test_generate_host import FakeEngine, per_step_reference
+
+    spec = importlib.util.spec_from_file_location("ref_mm_utils", os.path.join(REF, "llava", "mm_utils.py"))
+    mu = importlib.util.module_from_spec(spec)
+    sys.modules.setdefault("llava.constants", __import__("llava.constants", fromlist=["x"]))
+    spec.loader.exec_module(mu)
+
+    class Tok:
+        bos_token_id = 1
+
+        def __call__(self, text):
+            return type("Enc", (), {"input_ids": [1] + [ord(c) - 97 for c in text]})()
+
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return ["".join(chr(97 + int(i) % 26) if int(i) >= 0 else "?" for i in row) for row in ids]
+
+    prompt = torch.tensor([[1, 5, -200, 7, 9]])
+    free = per_step_reference([4], 40, set(), 0)[0].tolist()           # what the fake model generates unconstrained
+    text = "".join(chr(97 + t % 26) for t in free)
+    keyword = text[6:9]
+    stop_at = text.find(keyword) + 3
+    crit = mu.KeywordsStoppingCriteria([keyword], Tok(), prompt)
+    assert crit.start_len == 5
+    out = _stream_decode(FakeEngine([4]), None, None, None, 1, 40, set(), 0, prompt, None, [crit], run_ahead=8)
+    assert out[0].tolist() == free[:stop_at]

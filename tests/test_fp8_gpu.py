@@ -1,17 +1,9 @@
-"""GPU: the fp8 decode path (BASELINE configs[4]) against oracle/fp8_oracle.py, through the C ABI.
-
-These kernels were written at the end of round 1 AFTER the round's GPU budget was spent: they compile for sm_100a and the
-arithmetic they implement is pinned on the CPU (tests/test_fp8_oracle.py), but they have not run on a B200 yet. Until they
-have, the tests only run with B2_TEST_FP8=1 — the default GPU suite must stay a statement about validated code."""
-import math
-import os
-
+"""GPU: the fp8 decode path (BASELINE configs[4]) against oracle/fp8_oracle.py, through the C ABI (first executed on a
+B200 in round 2: profiles/r2a_fp8_2cta_first_run.txt)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B2_TEST_FP8") != "1",
-                                 reason="fp8 decode path not yet validated on a GPU: run with B2_TEST_FP8=1")]
+pytestmark = pytest.mark.gpu
 
 from llava import _b2  # noqa: E402
 from oracle import fp8_oracle as F  # noqa: E402
@@ -45,7 +37,13 @@ def test_quantize_rows_bit_exact(rows, K):
     q, s = quantize(x)
     qr, sr = F.quantize_rows_e4m3(x.cpu())
     assert torch.equal(s.cpu(), sr)
-    assert torch.equal(q.cpu(), qr.view(torch.uint8))
+    qg, qc = q.cpu(), qr.view(torch.uint8)
+    bad = (qg != qc).nonzero()
+    if len(bad):  # say WHAT differs: value, scaled value, both codes
+        inv = torch.where(sr > 0, 448.0 / (sr * 448.0), torch.ones_like(sr))
+        lines = [f"x={float(x[r, c]):.9g} scaled={float(x[r, c].float().cpu() * (448.0 / x[r].float().abs().max().cpu())):.9g} "
+                 f"gpu={int(qg[r, c])} cpu={int(qc[r, c])}" for r, c in bad[:12].tolist()]
+        pytest.fail(f"{len(bad)} of {qg.numel()} e4m3 codes differ:\n" + "\n".join(lines))
 
 
 def test_rmsnorm_quant_matches_restatement():
@@ -102,7 +100,15 @@ def test_gemm_skinny_fp8_swiglu_and_residual():
     qw, sw = quantize(wgu)
     got = skinny_fp8(qx, sx, qw, sw, act=_b2.ACT_SWIGLU)
     want = F.swiglu_w8a8(x.cpu(), wg.cpu(), wu.cpu())
-    torch.testing.assert_close(got.cpu().float(), want.float(), rtol=2e-2, atol=2e-2 * float(want.float().abs().mean()))
+    # Error model: gate and up each carry an accumulation error delta ~ 2e-3 of their RMS (the plain-GEMM test's bound: the
+    # tensor core's fp32 accumulation of e4m3 products is not bit-identical to a sequential fp32 sum), which
+    # silu(g) * u turns into |silu'(g)| |u| delta + |silu(g)| delta — NOT small relative to the output where u or silu(g)
+    # is small while the other factor is large — plus one bf16 rounding of the result.
+    g_ref, u_ref = F.linear_fake_quant(x.cpu(), wg.cpu()), F.linear_fake_quant(x.cpu(), wu.cpu())
+    delta = 2e-3 * float(g_ref.pow(2).mean().sqrt())
+    tol = delta * (1.1 * u_ref.abs() + torch.nn.functional.silu(g_ref).abs()) + 2 ** -7 * want.float().abs() + 1e-6
+    err = (got.cpu().float() - want.float()).abs()
+    assert bool((err <= tol).all()), f"max err/tol {float((err / tol).max()):.2f} at {int((err / tol).argmax())}"
     r = torch.randn(B, 2 * I, device=DEV).to(BF)
     got_r = skinny_fp8(qx, sx, qw, sw, residual=r, out_fp32=True)
     want_r = F.linear_w8a8(qx.cpu().view(torch.float8_e4m3fn), sx.cpu(), qw.cpu().view(torch.float8_e4m3fn), sw.cpu(), r.cpu())

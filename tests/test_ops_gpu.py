@@ -133,12 +133,7 @@ def test_gemm_linearity_and_determinism():
     assert torch.equal(gemm(A1, W, out_fp32=True), c1)
 
 
-# ------------------------------------------------------------------------- CTA-pair (cta_group::2) GEMM — draft
-_pair = pytest.mark.skipif(__import__("os").environ.get("B2_TEST_2CTA") != "1",
-                           reason="gemm_2cta.cu was written without GPU access (end of round 1): run with B2_TEST_2CTA=1")
-
-
-@_pair
+# ------------------------------------------------------------------------- CTA-pair (cta_group::2) GEMM
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 512), (704, 4096, 4096), (9232, 3072, 1024),
                                    (9232, 1024, 4096), (5632, 12288, 4096), (300, 136, 264)])
 def test_gemm_2cta_plain(M, N, K):
@@ -146,7 +141,6 @@ def test_gemm_2cta_plain(M, N, K):
     assert_close(gemm(A, W, bn=2), ref_linear(A, W))
 
 
-@_pair
 def test_gemm_2cta_epilogues_match_the_1cta_kernel():
     M, N, K = 1154, 4096, 1024
     A, W, b, r = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(N), rnd(M, N)
