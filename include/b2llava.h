@@ -91,8 +91,8 @@ int b2_model_destroy(b2_model* m);
 /* BASELINE configs[4] ("fp8-weight tcgen05 path"): after finalize, quantise the decoder's Linear weights to e4m3 with one
  * fp32 scale per output channel; decode steps at batch >= 7 then run e4m3 x e4m3 tcgen05 GEMMs (activations quantised
  * per token on the fly, KV cache stays bf16). Prefill and small-batch decode keep the bf16 weights. The reference has no
- * fp8 path; oracle/fp8_oracle.py defines the arithmetic and the tolerance. NOT YET VALIDATED ON A GPU (drafted at the end
- * of round 1 after the GPU budget was spent): off unless this call is made. */
+ * fp8 path; oracle/fp8_oracle.py defines the arithmetic and the tolerance (tests/test_fp8_gpu.py). Off unless this call is
+ * made: it changes the numerics of the decode step (W8A8), so it is never a default. */
 int b2_model_enable_fp8_decode(b2_model* m);
 
 int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out); /* KV cache [L][2][B][H][Smax][128] bf16 */

@@ -1,8 +1,8 @@
 // CTA-pair (cta_group::2) bf16 GEMM for the big-M launches (ViT at B >= 16, LLaMA prefill at B >= 8):
 //     C[M,N] = epilogue(A[M,K] · W[N,K]^T)          one 256 x 256 output tile per CTA PAIR
 //
-// [DRAFT — written at the end of round 1 after the GPU budget was spent: it assembles for sm_100a (UTCHMMA.2CTA in the SASS)
-//  but has never run. Off unless B2_GEMM_2CTA=1; tests/test_ops_gpu.py::test_gemm_2cta_* run with that variable set.]
+// Selected by gemm_bf16's cost model (gemm_tcgen05.cu) wherever its pair tiles fill their waves; first run on a B200 in
+// round 2 (tests/test_ops_gpu.py::test_gemm_2cta_*), measured in profiles/r2b_gemm_sweep.json.
 //
 // Why: the 1-CTA kernel (gemm_tcgen05.cu) reads 96 B/clk of operands from shared memory at its best tile (128x256) — every
 // CTA stages the whole 256-row B tile — and tops out at 75-90 % of cuBLAS on these shapes (profiles/r1e_gemm_sweep_bn192.json).

@@ -17,7 +17,7 @@
 //   * FP8 variant (template flag): e4m3 weights (per-output-channel fp32 scale) x e4m3 activations (per-token fp32 scale),
 //     tcgen05.mma kind::f8f6f4 (K = 32 per instruction, 128 elements per 128-byte swizzle row), dequantisation
 //     acc * w_scale[n] * x_scale[b] in the epilogue — BASELINE configs[4] ("fp8-weight tcgen05 path"): halves the weight
-//     stream. Same pipeline, same stream-K reduction. [drafted without GPU access at the end of round 1: not yet validated]
+//     stream. Same pipeline, same stream-K reduction.
 // Replaces, for B > 8, the HF one-token Linear calls (transformers modeling_llama.py:251-289 q/k/v/o_proj, :182-184
 // LlamaMLP, :486-487 lm_head) behind the reference's decode branch (llava/model/llava_arch.py:103-112).
 #include <cuda.h>

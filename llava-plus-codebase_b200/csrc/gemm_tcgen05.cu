@@ -407,17 +407,16 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                      ((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ld_res % 8) == 0),
                  "gemm: residual must be 16B aligned with ld_res %% 8 == 0");
 
-    // CTA-pair kernel (draft, never run on a GPU yet): only on request
-    if (g.bn_override == 2) return gemm_bf16_2cta(g, stream);
-    if (g.bn_override == 0 && g.M >= 1024 && g.N >= 512) {
-        const char* e = getenv("B2_GEMM_2CTA");
-        if (e != nullptr && e[0] == '1') return gemm_bf16_2cta(g, stream);
-    }
+    if (g.bn_override == 2) return gemm_bf16_2cta(g, stream);  // CTA-pair kernel (cta_group::2, 256x256 pair tiles)
 
     // Tile-N choice. Cost model fitted to profiles/r1b_gemm_sweep.json: a tile costs ~BN / rel(BN) (rel = tensor-pipe
     // feed efficiency of the shape: BN=256 needs 96 B/clk of smem operand traffic, BN=128 sits on the 128 B/clk limit,
     // BN=64 is far over it) and the launch takes ceil(tiles / #SMs) waves. BN=192 exists for the N=4096 projections of a
     // B=1 prefill (M=704): 96 tiles of 256 leave a third of the SMs idle, 132 tiles of 192 fill one wave.
+    // The CTA-pair kernel competes as a fifth shape: a 256x256 pair tile is per-SM the work of a 128x256 tile with half the
+    // B-operand smem traffic; measured 4-10 % above BN=256 wherever it fills its waves (profiles/r2b_gemm_sweep.json: 7B
+    // prefill qkv 1146 -> 1237, gate/up 1157 -> 1255 TFLOP/s at M=704; 1322 -> 1442 / 1410 -> 1556 at M=5632; ViT fc2 at B=64
+    // 1389 -> 1488), and behind BN=192 where 48 pair tiles leave two thirds of the pairs idle (N=4096 projections at M=704).
     const int num_m = (g.M + BM - 1) / BM;
     int bn = 64;
     {
@@ -430,6 +429,13 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
             const long long waves = (tiles + num_sms() - 1) / num_sms();
             const float cost = (float)waves * ((float)cand[i] / rel[i] + 24.f /*per-tile fixed cost*/);
             if (best == 0.f || cost < best) { best = cost; bn = cand[i]; }
+        }
+        if (g.bn_override == 0 && g.M >= 512 && g.N >= 256) {
+            const long long pairs = (long long)((g.M + 255) / 256) * ((g.N + 255) / 256);
+            const long long pair_slots = num_sms() / 2;
+            const long long waves = (pairs + pair_slots - 1) / pair_slots;
+            const float cost = (float)waves * (256.f / 1.08f + 24.f);
+            if (cost < best) return gemm_bf16_2cta(g, stream);
         }
     }
     if (g.bn_override == 64 || g.bn_override == 128 || g.bn_override == 192 || g.bn_override == 256) bn = g.bn_override;

@@ -23,10 +23,10 @@ struct GemmArgs {
     void* out = nullptr; int ld_out = 0; int out_fp32 = 0;
     int M = 0, N = 0, K = 0;
     int act = ACT_NONE;
-    int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256 (2 = CTA-pair kernel, draft)
+    int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256 (2 = CTA-pair kernel)
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
-// CTA-pair (cta_group::2, 256x256 pair tiles) variant, gemm_2cta.cu [unvalidated draft: B2_GEMM_2CTA=1 or bn_override == 2]
+// CTA-pair (cta_group::2, 256x256 pair tiles) variant, gemm_2cta.cu (chosen by gemm_bf16's cost model, or bn_override == 2)
 int gemm_bf16_2cta(const GemmArgs& g, cudaStream_t stream);
 
 // ---- swap-AB stream-K GEMM for decode at batch 9..128 (gemm_skinny.cu) ------------------------------------
@@ -44,11 +44,11 @@ struct SkinnyArgs {
     const float* x_scale = nullptr;              // fp8 variant: [B] per token
 };
 int gemm_skinny_bf16(const SkinnyArgs& g, cudaStream_t stream);
-int gemm_skinny_fp8(const SkinnyArgs& g, cudaStream_t stream);   // [unvalidated draft, see gemm_skinny.cu]
+int gemm_skinny_fp8(const SkinnyArgs& g, cudaStream_t stream);
 size_t gemm_skinny_workspace_bytes(int B, int N, int K);
 size_t gemm_skinny_counter_bytes(int N);
 
-// ---- e4m3 row quantisation for the fp8 decode path (quant_fp8.cu) [unvalidated draft] ----------------------
+// ---- e4m3 row quantisation for the fp8 decode path (quant_fp8.cu) ----------------------
 // scale[r] = amax_r / 448 (1 for a zero row); q[r,k] = e4m3_rn_satfinite(x[r,k] * (448 / amax_r)); ld* in elements
 int quantize_rows_e4m3(const void* x, int64_t ldx, int rows, int K, void* q, int64_t ldq, float* scale, cudaStream_t stream);
 // RMSNorm (HF rounding points) fused with the per-token quantisation of its output

@@ -7,7 +7,7 @@
 // here) and (b) per decode step on the activations (per-TOKEN scales), fused with RMSNorm where the GEMM input is a
 // normed hidden state. The reference has no fp8 path: the test suite carries a CPU restatement of exactly these two
 // formulas (torch.float8_e4m3fn, round-to-nearest-even) and derives the tolerance of the whole path against the bf16
-// path from it. [drafted without GPU access at the end of round 1: not yet validated on a B200]
+// path from it.
 #include <cuda_fp8.h>
 
 #include "common.cuh"

@@ -230,7 +230,7 @@ class Engine:
         self.finalized = True
 
     def enable_fp8_decode(self):
-        """BASELINE configs[4]: e4m3 weights for decode at batch >= 7 (see include/b2llava.h; unvalidated draft)."""
+        """BASELINE configs[4]: e4m3 weights for decode at batch >= 7 (see include/b2llava.h): W8A8 numerics, opt-in."""
         with torch.cuda.device(self.index):
             check(self.lib.b2_model_enable_fp8_decode(self.handle), "b2_model_enable_fp8_decode")
 

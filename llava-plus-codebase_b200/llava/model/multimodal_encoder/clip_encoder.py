@@ -94,6 +94,23 @@ def _read_checkpoint_dir(path):
     return sd
 
 
+def _resolve_checkpoint_dir(name):
+    """Local directory of a checkpoint named like the reference names its tower (ref clip_encoder.py:22-27 hands the name
+    to `from_pretrained`): an existing directory is used as is; a hub id such as `openai/clip-vit-large-patch14-336` (what a
+    stock llava-v1.5 config.json carries in `mm_vision_tower`, ref builder.py:140-144) resolves through the local
+    HuggingFace cache. Nothing is downloaded here."""
+    if os.path.isdir(name):
+        return name
+    try:
+        from huggingface_hub import snapshot_download
+        return snapshot_download(name, local_files_only=True)
+    except Exception as e:
+        raise RuntimeError(
+            f"vision tower {name!r} is neither a local directory nor present in the local HuggingFace cache "
+            f"(HF_HOME / HF_HUB_CACHE); this path never downloads: populate the cache (`huggingface-cli download {name}`) "
+            f"or point mm_vision_tower at a directory with config.json, preprocessor_config.json and the weights") from e
+
+
 class CLIPVisionTower(nn.Module):
     def __init__(self, vision_tower, args, delay_load=False):
         super().__init__()
@@ -118,12 +135,12 @@ class CLIPVisionTower(nn.Module):
         cfg = CLIPVisionConfig.from_pretrained(self.vision_tower_name)
         self.vision_tower = _CLIPVisionWeights(cfg)
         if not random_init:
-            sd = _read_checkpoint_dir(self.vision_tower_name) if os.path.isdir(self.vision_tower_name) else {}
-            sd = {k: v for k, v in sd.items() if k.startswith("vision_model.")}
+            ckpt_dir = _resolve_checkpoint_dir(self.vision_tower_name)
+            sd = {k: v for k, v in _read_checkpoint_dir(ckpt_dir).items() if k.startswith("vision_model.")}
             if not sd:
                 raise RuntimeError(
-                    f"no CLIP vision weights found under {self.vision_tower_name!r} (offline: pass a local directory "
-                    f"with model.safetensors / pytorch_model.bin, or use load_model(random_init=True))")
+                    f"no CLIP vision weights (vision_model.*) found under {ckpt_dir!r}: expected model.safetensors / "
+                    f"pytorch_model.bin of a CLIPModel or CLIPVisionModel checkpoint")
             missing, unexpected = self.vision_tower.load_state_dict(sd, strict=False)
             missing = [k for k in missing if "position_ids" not in k]
             if missing:

@@ -23,7 +23,9 @@ def quantize_rows_e4m3(x: torch.Tensor):
     xf = x.float()
     amax = xf.abs().amax(dim=-1)
     pos = amax > 0
-    inv = torch.where(pos, E4M3_MAX / amax, torch.ones_like(amax))
+    # tensor / tensor: IEEE division like the kernel's `448.0f / amax` (torch evaluates `scalar / tensor` as scalar * reciprocal,
+    # which is 1 ulp off for e.g. amax = 12 and flips exact ties such as 4.5 * 448/12 = 168 between the codes 160 and 176)
+    inv = torch.where(pos, torch.full_like(amax, E4M3_MAX) / amax, torch.ones_like(amax))
     scale = torch.where(pos, amax / E4M3_MAX, torch.ones_like(amax))
     q = (xf * inv.unsqueeze(-1)).to(torch.float8_e4m3fn)
     return q, scale

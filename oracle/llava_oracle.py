@@ -118,6 +118,31 @@ def make_weights(cfg, seed=0, dtype=torch.float32):
     return w
 
 
+def condition_weights(w, cfg, seed=0, layer_gain=None):
+    """Well-conditioned variant of a weight set for STRICT greedy-id tests. Under plain random init the
+    top-1/top-2 logit margin is of the order of the bf16 noise, so identical ids would be luck. Here the output head is
+    tied to a permutation of the embedding table (lm_head[perm[t]] = embed_tokens[t]) and the residual branches
+    (o_proj, down_proj) are damped by `layer_gain`, so the final hidden state keeps a cosine of ~0.3-0.5 with the embedding
+    of the token that was fed: the winning logit stands ~|e|^2 cos above a field of ~N(0, |e|^2 / h) competitors — tens of
+    noise widths — while every layer still shapes the state (attention over the whole context and the MLPs contribute
+    the other ~70-95 % of its norm). Greedy ids are then a deterministic, noise-robust function of the model: any two
+    correct implementations must produce the same ids. Returns a NEW dict (tensors not scaled are shared)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    V = cfg["vocab"]
+    if layer_gain is None:
+        layer_gain = min(1.0, 2.0 / math.sqrt(2.0 * cfg["layers"]))  # residual grows to ~ sqrt(1 + 4) of the embedding norm
+    out = dict(w)
+    perm = torch.randperm(V, generator=g)
+    head = torch.empty_like(w["lm_head.weight"])
+    head[perm] = w["model.embed_tokens.weight"].to(head.dtype)
+    out["lm_head.weight"] = head
+    for i in range(cfg["layers"]):
+        for k in ("self_attn.o_proj.weight", "mlp.down_proj.weight"):
+            key = f"model.layers.{i}.{k}"
+            out[key] = (w[key].float() * layer_gain).to(torch.bfloat16).to(w[key].dtype)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 # CLIP ViT + projector
 # ------------------------------------------------------------------------------------------------------
