@@ -118,6 +118,14 @@ int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* st
  * out of bounds: the row is zero-filled and the problem is reported by b2_async_error(). */
 int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, int n_feat_rows, int rows, void* embeds_out,
               void* stream);
+/* The whole splice on the device, for the layout every generation caller of the reference uses (equal-length rows without
+ * padding, k_per_row IMAGE_TOKEN_INDEX placeholders per row; llava/serve/model_worker.py:163, llava/eval/model_vqa_loader.py:98):
+ * input_ids int64 [B,Lt] stays on the device (no D2H of the ids, no host loop over rows — reference llava_arch.py:143-187);
+ * image slot j holds feature rows [feat_offsets_host[j], feat_offsets_host[j+1]) of image_feats, slots are consumed in
+ * row-major order. The caller derives S = Lt - k + rows-per-row from shapes alone. A row whose placeholder count is not
+ * k_per_row is flagged (b2_async_error code 4) and the caller redoes the splice on the exact host path (b2_splice). */
+int b2_splice_ids(b2_model* m, const int64_t* input_ids, int B, int Lt, int k_per_row, const int32_t* feat_offsets_host, int n_img,
+                  const void* image_feats, int S, void* embeds_out, void* stream);
 /* Input problems that only a kernel can see (ids live on the device): returns in *code_out the OR of 1 = token id outside
  * [0, vocab) or an image placeholder without features, 2 = image-feature row out of range, 4 = more placeholders than
  * images, accumulated since the last call, and clears it. Meaningful after the stream has been synchronised (the codes
@@ -129,6 +137,10 @@ int b2_async_error(b2_model* m, int* code_out);
  * B2_LOGITS_ALL -> fp32 [B,S,vocab] (the reference's lm_head over all positions, llava_llama.py:88-99). */
 int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_lens_host, int B, int S,
                void* logits_out, int logits_mode, void* stream);
+/* b2_prefill into the cache slots [slot0, slot0 + B) — the other slots of the cache are not touched (continuous batching:
+ * a new request is prefilled while the rest of the batch keeps its context). b2_prefill == slot0 0. */
+int b2_prefill_slots(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_lens_host, int B, int S, int slot0,
+                     void* logits_out, int logits_mode, void* stream);
 /* One autoregressive step (reference decode branch llava_arch.py:103-112 + HF one-token forward): tokens [B]
  * int32 (host or device) are embedded, run through the decoder against the cache (appending one K/V row per
  * layer), logits_out fp32 [B,vocab] (nullable), next_tokens_out int32 [B] = argmax (nullable, host or device). */
@@ -156,6 +168,16 @@ int b2_argmax(const float* logits, int B, int V, int32_t* out, void* stream);
 int b2_stream_begin(b2_model* m, b2_kv* kv, const float* logits, int B, const b2_sampling* sampling, void* stream);
 int b2_stream_enqueue(b2_model* m, b2_kv* kv, int n_steps, void* stream);
 int b2_stream_wait(b2_kv* kv, int index, int32_t* tokens_host, int timeout_ms);
+
+/* Continuous batching (the reference's worker runs up to limit_model_concurrency generate() threads on one
+ * model, llava/serve/model_worker.py:230-243, each a batch-1 HF loop; here they share ONE batched decode step). The B slots of
+ * a cache are a pool: b2_batch_begin puts the cache in per-slot mode (every slot idle, streaming ring armed);
+ * b2_prefill_slots fills one slot; b2_batch_set_row(active=1) arms it with its own sampling parameters and the token chosen
+ * from its prefill logits; b2_stream_enqueue(n) then advances ALL slots by n steps in one batched step each (idle slots keep
+ * their length and are ignored) and b2_stream_wait hands the step's B tokens to the host; b2_batch_set_row(active=0) frees a
+ * slot. Token selection is per slot: greedy or temperature/top-k/top-p with the slot's own Philox stream. */
+int b2_batch_begin(b2_model* m, b2_kv* kv, int B, void* stream);
+int b2_batch_set_row(b2_model* m, b2_kv* kv, int slot, int active, const b2_sampling* sampling, int first_token, void* stream);
 
 /* ---- single-kernel entry points (unit-level parity tests; same kernels the hot path launches) ----------- */
 int b2_op_gemm(const void* A, int lda, const void* W, int ldw, const void* bias, const void* residual, int ld_res,
@@ -197,6 +219,23 @@ int b2_op_decode_attn(const void* qkv, void* kcache, void* vcache, const int32_t
 int64_t b2_op_decode_attn_scratch_bytes(int B, int H, int nsplit); /* caller zero-fills the scratch once */
 int b2_op_interleave_gate_up(const void* gate, const void* up, void* out, int I, int h, void* stream);
 int b2_op_im2col(const void* pixels, void* out, int B, int img, int patch, int kpad, void* stream);
+/* Image preprocessing on the device (csrc/preprocess.cu): the reference's llava/mm_utils.py:16-44 (`expand2square` +
+ * CLIPImageProcessor.preprocess = PIL bicubic shortest-edge resize, centre crop, rescale, normalise) for ONE uint8 RGB image.
+ * The caller (llava/_b2/preprocess.py) supplies the resize plan: PIL's fixed-point coefficient tables for both axes
+ * (bounds[2*i] = first tap, bounds[2*i+1] = tap count, kk[i*ksize + t] = 22-bit fixed-point weight; *_identity != 0 when
+ * the axis is not resized), the virtual padding, the crop origin and the source-row window of the vertical pass. All
+ * pointers are device pointers. pixels: bf16 [3,out,out] (nullable); u8_out: uint8 [out,out,3] before normalisation (nullable). */
+typedef struct b2_preprocess_plan {
+    const uint8_t* img; int32_t H, W;
+    int32_t pad_top, pad_left; uint8_t bg[4];
+    const int32_t *h_bounds, *h_kk; int32_t h_ksize, h_identity;
+    const int32_t *v_bounds, *v_kk; int32_t v_ksize, v_identity;
+    int32_t y0, rows, x_lo, y_lo, out;
+    uint8_t* tmp;                /* scratch, >= rows*out*3 bytes */
+    float mean[3], stdv[3], rescale;
+    void* pixels; uint8_t* u8_out;
+} b2_preprocess_plan;
+int b2_op_preprocess_clip(const b2_preprocess_plan* plan, void* stream);
 /* one selection per row from fp32 logits [B,V] (csrc/sampling.cu): out_tokens device int32 [B]; `index` is the draw index
  * that keys the Philox stream (token position within a generation). Synchronises the stream. */
 int b2_op_sample(const float* logits, int B, int V, const b2_sampling* sampling, int index, int32_t* out_tokens, void* stream);

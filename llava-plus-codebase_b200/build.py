@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb2llava.so")
-SOURCES = ["gemm_tcgen05.cu", "gemm_2cta.cu", "gemm_skinny.cu", "quant_fp8.cu", "gemv.cu", "decode_mega.cu", "attention.cu", "attention_tc.cu", "norms.cu", "vit_ops.cu", "misc_ops.cu", "sampling.cu", "model.cu"]
+SOURCES = ["gemm_tcgen05.cu", "gemm_2cta.cu", "gemm_skinny.cu", "quant_fp8.cu", "gemv.cu", "decode_mega.cu", "attention.cu", "attention_tc.cu", "norms.cu", "vit_ops.cu", "misc_ops.cu", "sampling.cu", "preprocess.cu", "model.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -763,10 +763,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaParams p
                 const int tk = bi == INT_MAX ? 0 : bi;
                 p.tok[b] = tk;
                 p.out_tokens[(size_t)(*p.step_counter) * B + b] = tk;
-                p.cur_len[b] += 1;  // every attention phase of this launch is behind the last barrier
+                if (p.rows == nullptr || p.rows[b].active) p.cur_len[b] += 1;  // every attention phase of this launch is behind the last barrier
                 if (p.ring != nullptr) {  // streaming generate(): the host reads the token from mapped pinned memory
-                    const int pub = p.sstate->pub_counter, tag = p.sstate->tag;
-                    if (tag != 0) {
+                    const int pub = p.sstate->pub_counter, tag0 = p.sstate->tag;
+                    if (tag0 != 0) {
+                        const int tag = 1 + (tag0 - 1 + pub / p.ring_cap) % 2047;  // advances when the ring wraps (sampling.cu)
                         reinterpret_cast<volatile int32_t*>(p.ring)[(size_t)(pub % p.ring_cap) * B + b] = (tag << 20) | (tk & 0xFFFFF);
                         __threadfence_system();
                     }

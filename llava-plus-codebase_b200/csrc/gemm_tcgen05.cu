@@ -360,6 +360,198 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ---------------------------------------------------------------------------------------------
+// mm_projector as ONE kernel: out = (gelu_erf(X·W1^T + b1))·W2^T + b2   (reference: nn.Sequential(Linear, GELU, Linear),
+// llava/model/multimodal_projector/builder.py:39-46)
+// ---------------------------------------------------------------------------------------------
+// Same warp-specialised pipeline as gemm_bf16_tcgen05_kernel, but the persistent tile loop walks the tiles of BOTH GEMMs in
+// one dependency-ordered sequence:  P1(g0) P1(g1) P2(g0) P1(g2) P2(g1) ... P2(gLast)   (g = group of FP_GM row blocks).
+// A phase-2 tile of row block m needs the whole 128 x N1 slab of the intermediate H, i.e. all N1/BN phase-1 tiles of m: their
+// epilogue warps publish completion with st.global -> __threadfence -> atomicAdd(row_done[m]); the phase-2 TMA producer
+// acquires the counter, crosses from the generic to the async proxy (fence.proxy.async) and only then issues its loads.
+// Every dependency points backwards in the sequence and every CTA walks it in increasing order, so the spin cannot
+// deadlock (grid <= #SMs, one CTA per SM: all CTAs are resident). H never needs a second launch to become visible and, for
+// batches of images, is consumed one group (1024 rows = 8 MB) behind its production, out of L2.
+constexpr int FP_GM = 8;
+
+struct FusedProjParams {
+    int M, N1, K1, N2;       // K2 == N1
+    EpiParams ep1, ep2;      // ep1.out = H (bf16 [M, N1]); ep2.out = result
+    int* row_done;           // [ceil(M/128)] completion counters, zeroed (stream-ordered) before the launch
+    int target;              // value row_done[m] reaches when every epilogue warp of every phase-1 tile of row block m has arrived
+};
+
+struct FpTile { int phase, m_blk, n_blk; };
+
+__device__ __forceinline__ FpTile fp_tile(int t, int num_m, int nn1, int nn2) {
+    // sequence: P1(0) | P1(1) P2(0) | P1(2) P2(1) | ... | P2(G-1)
+    const int G = (num_m + FP_GM - 1) / FP_GM;
+    FpTile r;
+    for (int slot = 0; slot < 2 * G; ++slot) {
+        int phase, g;
+        if (slot == 0) { phase = 1; g = 0; }
+        else if (slot == 2 * G - 1) { phase = 2; g = G - 1; }
+        else { phase = (slot & 1) ? 1 : 2; g = (slot & 1) ? (slot + 1) / 2 : slot / 2 - 1; }
+        const int gs = min(FP_GM, num_m - g * FP_GM);
+        const int n = gs * (phase == 1 ? nn1 : nn2);
+        if (t < n) {
+            r.phase = phase;
+            r.m_blk = g * FP_GM + t % gs;
+            r.n_blk = t / gs;
+            return r;
+        }
+        t -= n;
+    }
+    r.phase = 0; r.m_blk = 0; r.n_blk = 0;
+    return r;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+projector_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                       const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w2,
+                       FusedProjParams P) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (P.M + BM - 1) / BM;
+    const int nn1 = (P.N1 + BN - 1) / BN, nn2 = (P.N2 + BN - 1) / BN;
+    const int total_tiles = num_m * (nn1 + nn2);
+    const int nkb1 = (P.K1 + BK - 1) / BK, nkb2 = (P.N1 + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_w1); tma_prefetch_desc(&tmap_h); tma_prefetch_desc(&tmap_w2);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kNumEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const FpTile tl = fp_tile(t, num_m, nn1, nn2);
+                if (tl.phase == 2) {
+                    // all phase-1 tiles of this row block have been stored and fenced by their CTAs
+                    unsigned int spins = 0;
+                    int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(P.row_done + tl.m_blk) : "memory");
+                        if (++spins > (1u << 26)) asm volatile("trap;");
+                    } while (seen - P.target < 0);
+                    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of H -> async-proxy (TMA) reads
+                }
+                const CUtensorMap* ta = tl.phase == 1 ? &tmap_x : &tmap_h;
+                const CUtensorMap* tb = tl.phase == 1 ? &tmap_w1 : &tmap_w2;
+                const int nkb = tl.phase == 1 ? nkb1 : nkb2;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, ta, &full_bar[stage], kb * BK, tl.m_blk * BM, kEvictNormal);
+                    tma_load_2d(sa + A_TILE_BYTES, tb, &full_bar[stage], kb * BK, tl.n_blk * BN, kEvictNormal);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+            int stage = 0; uint32_t phase = 0; int local = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+                const FpTile tl = fp_tile(t, num_m, nn1, nn2);
+                const int nkb = tl.phase == 1 ? nkb1 : nkb2;
+                const int as = local & 1;
+                mbar_wait(&tmem_empty[as], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == nkb - 1) umma_commit(&tmem_full[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..9: bias (+ erf-GELU in phase 1), bf16 stores; phase 1 publishes the row block =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int local = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            const FpTile tl = fp_tile(t, num_m, nn1, nn2);
+            const EpiParams& ep = tl.phase == 1 ? P.ep1 : P.ep2;
+            const int N = tl.phase == 1 ? P.N1 : P.N2;
+            const int as = local & 1;
+            mbar_wait(&tmem_full[as], (local >> 1) & 1);
+            tc_fence_after();
+            const int row = tl.m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < P.M;
+            const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+#pragma unroll 1
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr_row + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = tl.n_blk * BN + c * 32;
+#pragma unroll
+                for (int v8 = 0; v8 < 4; ++v8) {
+                    const int col = col0 + v8 * 8;
+                    if (!(row_ok && col < N)) continue;
+                    float x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[v8 * 8 + e]);
+                    const uint4 b = *reinterpret_cast<const uint4*>(ep.bias + col);
+                    x[0] += bf16_lo(b.x); x[1] += bf16_hi(b.x); x[2] += bf16_lo(b.y); x[3] += bf16_hi(b.y);
+                    x[4] += bf16_lo(b.z); x[5] += bf16_hi(b.z); x[6] += bf16_lo(b.w); x[7] += bf16_hi(b.w);
+                    if (tl.phase == 1) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x[e] = act_gelu_erf(x[e]);
+                    }
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ld_out + col;
+                    *reinterpret_cast<uint4*>(op) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                                                               pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+                }
+            }
+            tc_fence_before();
+            if (tl.phase == 1) {
+                __threadfence();  // this lane's H stores are visible device-wide before the warp's arrival below
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tmem_empty[as]);
+                if (tl.phase == 1) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(P.row_done + tl.m_blk) : "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN, int ACT>
@@ -392,7 +584,52 @@ int dispatch_act(int act, const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     return -1;
 }
 
+template <int BN>
+int launch_fused_projector(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& th, const CUtensorMap& tw2,
+                           const FusedProjParams& P, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    auto kern = projector_fused_kernel<BN>;
+    if (!attr_set) {
+        B2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_m = (P.M + BM - 1) / BM;
+    const int tiles = num_m * ((P.N1 + BN - 1) / BN + (P.N2 + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();  // <= #SMs, 1 CTA/SM: every CTA is resident (the spin needs it)
+    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(tx, tw1, th, tw2, P);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace
+
+// out[M,N2] = (gelu_erf(X[M,K1]·W1[N1,K1]^T + b1))·W2[N2,N1]^T + b2 in one launch; H [M,N1] bf16 is the caller's scratch,
+// row_done the caller's int[ceil(M/128)] scratch (zeroed here, on the stream).
+int projector_fused_bf16(const void* X, int ldx, const void* W1, const void* b1, const void* W2, const void* b2, void* H,
+                         void* out, int ld_out, int M, int K1, int N1, int N2, int* row_done, cudaStream_t stream) {
+    B2_CHECK_ARG(M > 0 && K1 % 8 == 0 && N1 % 8 == 0 && N2 % 8 == 0 && b1 && b2 && row_done,
+                 "projector_fused: bad problem M=%d K1=%d N1=%d N2=%d", M, K1, N1, N2);
+    const int num_m = (M + BM - 1) / BM;
+    // tile width: one wave of 192-wide tiles for a single image (5 row blocks x 22 = 110 tiles per GEMM), 256 otherwise
+    const int bn = (num_m * ((N1 + 191) / 192) <= num_sms()) ? 192 : 256;
+    CUtensorMap tx, tw1, th, tw2;
+    B2_TRY(make_tmap_bf16(&tx, X, M, K1, ldx, BM));
+    B2_TRY(make_tmap_bf16(&tw1, W1, N1, K1, K1, bn));
+    B2_TRY(make_tmap_bf16(&th, H, M, N1, N1, BM));
+    B2_TRY(make_tmap_bf16(&tw2, W2, N2, N1, N1, bn));
+    FusedProjParams P;
+    P.M = M; P.N1 = N1; P.K1 = K1; P.N2 = N2;
+    P.ep1.bias = reinterpret_cast<const __nv_bfloat16*>(b1); P.ep1.residual = nullptr; P.ep1.out = H; P.ep1.ld_out = N1;
+    P.ep1.ld_res = 0; P.ep1.out_fp32 = 0;
+    P.ep2.bias = reinterpret_cast<const __nv_bfloat16*>(b2); P.ep2.residual = nullptr; P.ep2.out = out; P.ep2.ld_out = ld_out;
+    P.ep2.ld_res = 0; P.ep2.out_fp32 = 0;
+    P.row_done = row_done;
+    P.target = ((N1 + bn - 1) / bn) * kNumEpiWarps;
+    B2_CUDA_CHECK(cudaMemsetAsync(row_done, 0, (size_t)num_m * sizeof(int), stream));
+    if (bn == 192) return launch_fused_projector<192>(tx, tw1, th, tw2, P, stream);
+    return launch_fused_projector<256>(tx, tw1, th, tw2, P, stream);
+}
 
 // C[M, N(/2 for swiglu)] = epi(A[M,K](lda) · W[N,K](ldw)^T). See kernels.h for the contract.
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {

@@ -26,6 +26,10 @@ struct GemmArgs {
     int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256 (2 = CTA-pair kernel)
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+// mm_projector mlp2x_gelu as ONE kernel (gemm_tcgen05.cu, projector_fused_kernel): out = gelu_erf(X W1^T + b1) W2^T + b2.
+// H [M,N1] bf16 and row_done int[ceil(M/128)] are caller scratch.
+int projector_fused_bf16(const void* X, int ldx, const void* W1, const void* b1, const void* W2, const void* b2, void* H,
+                         void* out, int ld_out, int M, int K1, int N1, int N2, int* row_done, cudaStream_t stream);
 // CTA-pair (cta_group::2, 256x256 pair tiles) variant, gemm_2cta.cu (chosen by gemm_bf16's cost model, or bn_override == 2)
 int gemm_bf16_2cta(const GemmArgs& g, cudaStream_t stream);
 
@@ -148,6 +152,7 @@ struct MegaParams {
     struct SampleState* sstate = nullptr;
     int32_t* ring = nullptr;
     int ring_cap = 0;
+    const struct RowState* rows = nullptr;  // continuous batching: only active slots advance their cache length
 };
 // one launch = embed -> all layers -> lm_head -> argmax -> token store; cur_len/step_counter advance on device
 int decode_mega(const MegaParams& p, cudaStream_t stream);
@@ -164,14 +169,40 @@ struct SampleState {
     int tag;                  // generation epoch 1..2047 published with every token; 0 = do not publish to the host ring
     int pub_counter;          // index of the next token of this generation
     unsigned int done;        // rows finished in the current launch (self-resetting)
+    int per_row;              // continuous batching: selection parameters and liveness come from RowState[b] instead
+};
+// One cache slot of a continuously batched decode (llava/_b2/batching.py): requests join and leave between steps, each with
+// its own sampling parameters and its own Philox draw index; a slot that is not active keeps its cache length and token.
+struct RowState {
+    int active;
+    int do_sample; float temperature, top_p; int top_k;
+    unsigned long long seed;
+    int index;                // draws made for this request so far
 };
 enum { SP_SELECT = 1,     // choose from `logits` (argmax or sample) and write tok[b]; otherwise tok[b] is already chosen
        SP_WRITE_OUT = 2,  // out_tokens[(*step_counter + step_offset) * B + b] = token
        SP_BUMP = 4 };     // last row: *step_counter += 1, cur_len[b] += 1
 int sample_state_set(SampleState* st_dev, const SampleState& v, cudaStream_t stream);
-int sample_publish(const float* logits, int V, int B, SampleState* st_dev, int32_t* tok, int32_t* out_tokens,
+int sample_publish(const float* logits, int V, int B, SampleState* st_dev, RowState* rows_dev, int32_t* tok, int32_t* out_tokens,
                    int32_t* step_counter, int32_t* cur_len, int32_t* ring_dev, int ring_cap, int flags, int step_offset,
                    cudaStream_t stream);
+int row_state_set(RowState* row_dev, const RowState& v, int32_t* tok_dev, int token, cudaStream_t stream);
+
+// ---- image preprocessing (preprocess.cu): uint8 HWC -> CLIP pixel_values, PIL-exact bicubic resize ------------------------
+struct PreprocessArgs {
+    const uint8_t* img = nullptr; int H = 0, W = 0;        // device, RGB HWC
+    int pad_top = 0, pad_left = 0; uint8_t bg[3] = {0, 0, 0};  // virtual expand2square: reads outside the image return bg
+    const int32_t *h_bounds = nullptr, *h_kk = nullptr; int h_ksize = 0, h_identity = 0;  // tables over the resized WIDTH
+    const int32_t *v_bounds = nullptr, *v_kk = nullptr; int v_ksize = 0, v_identity = 0;  // tables over the resized HEIGHT
+    int y0 = 0, rows = 0;        // source rows the vertical pass reads: [y0, y0 + rows)
+    int x_lo = 0, y_lo = 0;      // centre-crop origin inside the resized image
+    int cols = 0, out = 0;       // cols == out: crop width / output size
+    uint8_t* tmp = nullptr;      // [rows, cols, 3] scratch
+    float mean[3] = {0, 0, 0}, stdv[3] = {1, 1, 1}, rescale = 1.f / 255.f;
+    void* pixels = nullptr;      // bf16 [3, out, out] or null
+    uint8_t* u8_out = nullptr;   // uint8 [out, out, 3] (the resized + cropped image before normalisation) or null
+};
+int preprocess_clip_image(const PreprocessArgs& a, cudaStream_t stream);
 
 // ---- misc (misc_ops.cu) ----------------------------------------------------------------------------
 // out[r, :] = src_index[r] >= 0 ? table[src_index[r]] : (src_index[r] == INT32_MIN ? 0 : feats[-src_index[r]-1]).
@@ -179,6 +210,10 @@ int sample_publish(const float* logits, int V, int B, SampleState* st_dev, int32
 // (mapped host memory, B2_ERR_* codes, may be null): nothing is ever read out of bounds.
 int splice_embed(const int32_t* src_index, const void* table, const void* feats, void* out, int rows, int h, int vocab,
                  int n_feat_rows, int* err_flag, cudaStream_t stream);
+// device-built source index for equal-length unpadded rows with k_per_row image placeholders each (misc_ops.cu):
+// ids int64 [B, Lt] on the device; feat_offsets_host[n_img + 1] = prefix sums of the feature rows of the image slots
+int splice_index(const long long* ids, int B, int Lt, int k_per_row, const int32_t* feat_offsets_host, int n_img, int image_token,
+                 int S, int32_t* src_index, int* err_flag, cudaStream_t stream);
 int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab, int* err_flag,
                  cudaStream_t stream);
 enum { B2_ERR_TOKEN_RANGE = 1, B2_ERR_IMAGE_ROW_RANGE = 2, B2_ERR_SPLICE_SLOTS = 4 };

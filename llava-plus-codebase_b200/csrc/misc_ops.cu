@@ -128,6 +128,60 @@ __global__ void store_token_kernel(const int32_t* __restrict__ src, int32_t* __r
     if (b < B) dst_base[(size_t)(*step_counter) * B + b] = src[b];
 }
 
+// Device half of the splice INDEX (llava/model/llava_arch.py:143-187 of the reference, equal-length unpadded rows): one CTA
+// per prompt row scans the ids for IMAGE_TOKEN_INDEX with a block-wide prefix count and writes, for every output position
+// of the row, the source row that splice_embed_kernel gathers: token id for text, -(feature row)-1 for the image span.
+// Image slots are consumed in row-major order (row b owns slots b*k .. b*k+k-1, k = placeholders per row as the caller
+// expects them: a different count is reported through err_flag[B2_ERR_SPLICE_SLOTS] and the host redoes the splice on its
+// exact path). Output positions beyond S (cannot happen when the count matches) are dropped; nothing is written out of bounds.
+__global__ void __launch_bounds__(256)
+splice_index_kernel(const long long* __restrict__ ids, int Lt, int k_expected, I32Pack feat_off, int image_token, int S,
+                    int32_t* __restrict__ src_index, int* err_flag) {
+    __shared__ int s_warp[8];
+    __shared__ int s_total;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const long long* row = ids + (size_t)b * Lt;
+    const int chunk = (Lt + 255) / 256;
+    const int lo = min(tid * chunk, Lt), hi = min(lo + chunk, Lt);
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) mine += row[i] == (long long)image_token;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += up;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
+    if (tid == 255) s_total = base + incl;
+    int c = base + incl - mine;  // placeholders before position lo
+    const int slot0 = b * k_expected;
+    int32_t* out = src_index + (size_t)b * S;
+    // positions the row does not cover are zero rows (INT32_MIN): only reachable when the placeholder count is wrong
+    for (int i = tid; i < S; i += 256) out[i] = INT_MIN;
+    __syncthreads();
+    for (int i = lo; i < hi; ++i) {
+        const long long id = row[i];
+        const int cc = min(c, k_expected);
+        const int pos = (i - c) + (feat_off.v[slot0 + cc] - feat_off.v[slot0]);
+        if (id == (long long)image_token) {
+            if (c < k_expected) {
+                const int f0 = feat_off.v[slot0 + c], f1 = feat_off.v[slot0 + c + 1];
+                for (int f = f0; f < f1; ++f)
+                    if (pos + (f - f0) < S) out[pos + (f - f0)] = -f - 1;
+            }
+            ++c;
+        } else if (pos < S) {
+            // ids that do not fit an int32 can only be invalid: map them to an out-of-range index (reported by the gather)
+            out[pos] = (id >= 0 && id < 0x7fffffffLL) ? (int32_t)id : 0x7fffffff;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_total != k_expected && err_flag) report_err(err_flag, B2_ERR_SPLICE_SLOTS);
+}
+
 // dst_a[off + i] = a.v[i], dst_b[off + i] = b.v[i]: small host vectors travel as kernel parameters (no pinned staging
 // buffer whose lifetime would force a stream sync in the caller)
 __global__ void set_i32_pairs_kernel(int32_t* dst_a, int32_t* dst_b, I32Pack a, I32Pack b, int n, int off) {
@@ -145,6 +199,17 @@ int set_i32_pairs(int32_t* dst_a, const int32_t* a_host, int32_t* dst_b, const i
         set_i32_pairs_kernel<<<1, 128, 0, stream>>>(dst_a, dst_b, pa, pb, c, off);
         B2_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+int splice_index(const long long* ids, int B, int Lt, int k_per_row, const int32_t* feat_offsets_host, int n_img, int image_token,
+                 int S, int32_t* src_index, int* err_flag, cudaStream_t stream) {
+    B2_CHECK_ARG(B >= 1 && Lt >= 1 && S >= 1 && k_per_row >= 0 && n_img == B * k_per_row && n_img + 1 <= 128,
+                 "splice_index: bad arguments B=%d Lt=%d S=%d k=%d n_img=%d (at most 127 image slots)", B, Lt, S, k_per_row, n_img);
+    I32Pack off;
+    for (int i = 0; i <= n_img; ++i) off.v[i] = feat_offsets_host[i];
+    splice_index_kernel<<<B, 256, 0, stream>>>(ids, Lt, k_per_row, off, image_token, S, src_index, err_flag);
+    B2_LAUNCH_CHECK();
     return 0;
 }
 

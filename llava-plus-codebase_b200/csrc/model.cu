@@ -94,9 +94,17 @@ struct b2_model {
     cudaStream_t ws_stream = nullptr;
     bool ws_valid = false;
     // ViT workspace (per chunk of max_images)
-    DevBuf v_col, v_patch, v_hidden, v_xn, v_qkv, v_attn, v_mlp, v_feats, p_mid;
+    DevBuf v_col, v_patch, v_hidden, v_xn, v_qkv, v_attn, v_mlp, v_feats, p_mid, p_done;
     // LLaMA workspace
-    DevBuf x, xn, qkv, attn, act, last_idx, xlast, logits;
+    DevBuf x, xn, qkv, attn, act, last_idx, xlast, logits, splice_idx;
+    // encode_images replays a CUDA graph per chunk size (~190 launches per image, 5-20 us each at B = 1: the host cannot
+    // keep the GPU fed launch by launch). Inputs/outputs are staged through fixed buffers so the captured pointers stay valid.
+    DevBuf enc_pixels, enc_out;
+    std::vector<cudaGraphExec_t> enc_graph;  // index = images in the chunk (0 = unused)
+    std::vector<char> enc_warm;              // an eager run has set the function attributes for this chunk size
+    cudaStream_t enc_stream = nullptr;       // capture is illegal on the legacy default stream: such callers run here
+    cudaEvent_t enc_fork = nullptr, enc_join = nullptr;
+    int enc_launches = 0;                    // kernels in one captured chunk (b2_launch_count bookkeeping)
     // fp8 decode (BASELINE configs[4]): e4m3 lm_head + scales, quantised activation row buffer + per-token scales
     bool fp8_decode = false;
     DevBuf lm_head8, s_head, xq8, xscale;
@@ -129,6 +137,8 @@ struct b2_kv {
     int ring_cap = 0;
     int epoch = 0;                 // generations started on this cache (tag = 1 + epoch % 2047)
     int stream_B = 0, stream_tag = 0, stream_scheduled = 0;  // streaming generation in progress: tokens scheduled so far
+    DevBuf rows_dev;               // RowState[max_batch] (continuous batching)
+    std::vector<RowState> rows_host;
     size_t layer_stride() const { return (size_t)max_batch * m->d.heads * max_seq * m->hd; }
 };
 
@@ -402,8 +412,68 @@ int project_rows(b2_model* m, const void* feats, int rows, void* out, cudaStream
         const int n = rows - r0 < max_rows ? rows - r0 : max_rows;
         const bf16* a = reinterpret_cast<const bf16*>(feats) + (size_t)r0 * D;
         bf16* o = reinterpret_cast<bf16*>(out) + (size_t)r0 * h;
-        B2_TRY(gemm(a, D, m->p0_w.p, D, m->p0_b.p, nullptr, 0, m->p_mid.p, h, 0, n, h, D, ACT_GELU_ERF, st));
-        B2_TRY(gemm(m->p_mid.p, h, m->p2_w.p, h, m->p2_b.p, nullptr, 0, o, h, 0, n, h, h, ACT_NONE, st));
+        const char* pf = getenv("B2_PROJECTOR_FUSED");  // =0 restores the two-launch form (A/B runs, read per call)
+        if (!(pf != nullptr && pf[0] == '0')) {
+            // north_star: "mm_projector as one fused GEMM->GELU->GEMM kernel" (phase-2 tiles gated on per-row-block counters)
+            B2_TRY(projector_fused_bf16(a, D, m->p0_w.p, m->p0_b.p, m->p2_w.p, m->p2_b.p, m->p_mid.p, o, h, n, D, h, h,
+                                        m->p_done.as<int>(), st));
+        } else {
+            B2_TRY(gemm(a, D, m->p0_w.p, D, m->p0_b.p, nullptr, 0, m->p_mid.p, h, 0, n, h, D, ACT_GELU_ERF, st));
+            B2_TRY(gemm(m->p_mid.p, h, m->p2_w.p, h, m->p2_b.p, nullptr, 0, o, h, 0, n, h, h, ACT_NONE, st));
+        }
+    }
+    return 0;
+}
+
+// vision tower + projector for one chunk of n <= max_images images: pixels -> out [n*P, hidden]. First call per chunk size runs
+// eagerly (function attributes, driver entry points), the second captures, later ones replay.
+int encode_chunk(b2_model* m, const void* pixels, int n, void* out, cudaStream_t st) {
+    const b2_model_desc& d = m->d;
+    const char* eg = getenv("B2_ENCODE_GRAPH");  // =0: launch by launch (A/B runs)
+    if (eg != nullptr && eg[0] == '0') {
+        B2_TRY(vit_forward_chunk(m, pixels, n, m->v_feats.p, st));
+        return project_rows(m, m->v_feats.p, n * m->P, out, st);
+    }
+    const size_t in_bytes = (size_t)n * 3 * d.image_size * d.image_size * 2, out_bytes = (size_t)n * m->P * d.hidden * 2;
+    cudaStream_t run = st;
+    if (st == nullptr || st == cudaStreamLegacy) {
+        if (m->enc_stream == nullptr) {
+            B2_CUDA_CHECK(cudaStreamCreateWithFlags(&m->enc_stream, cudaStreamNonBlocking));
+            B2_CUDA_CHECK(cudaEventCreateWithFlags(&m->enc_fork, cudaEventDisableTiming));
+            B2_CUDA_CHECK(cudaEventCreateWithFlags(&m->enc_join, cudaEventDisableTiming));
+        }
+        B2_CUDA_CHECK(cudaEventRecord(m->enc_fork, st));
+        B2_CUDA_CHECK(cudaStreamWaitEvent(m->enc_stream, m->enc_fork, 0));
+        run = m->enc_stream;
+    }
+    B2_CUDA_CHECK(cudaMemcpyAsync(m->enc_pixels.p, pixels, in_bytes, cudaMemcpyDeviceToDevice, run));
+    if (!m->enc_warm[n]) {
+        B2_TRY(vit_forward_chunk(m, m->enc_pixels.p, n, m->v_feats.p, run));
+        B2_TRY(project_rows(m, m->v_feats.p, n * m->P, m->enc_out.p, run));
+        m->enc_warm[n] = 1;
+    } else {
+        if (m->enc_graph[n] == nullptr) {
+            cudaGraph_t graph = nullptr;
+            B2_CUDA_CHECK(cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal));
+            const unsigned long long launches_before = g_launch_count;
+            int r = vit_forward_chunk(m, m->enc_pixels.p, n, m->v_feats.p, run);
+            if (r == 0) r = project_rows(m, m->v_feats.p, n * m->P, m->enc_out.p, run);
+            m->enc_launches = (int)(g_launch_count - launches_before);
+            g_launch_count = launches_before;  // capture records launches, it does not run them
+            cudaError_t e = cudaStreamEndCapture(run, &graph);
+            if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+            B2_CUDA_CHECK(e);
+            e = cudaGraphInstantiate(&m->enc_graph[n], graph, 0);
+            cudaGraphDestroy(graph);
+            B2_CUDA_CHECK(e);
+        }
+        B2_CUDA_CHECK(cudaGraphLaunch(m->enc_graph[n], run));
+        g_launch_count += (unsigned long long)m->enc_launches;
+    }
+    B2_CUDA_CHECK(cudaMemcpyAsync(out, m->enc_out.p, out_bytes, cudaMemcpyDeviceToDevice, run));
+    if (run != st) {
+        B2_CUDA_CHECK(cudaEventRecord(m->enc_join, run));
+        B2_CUDA_CHECK(cudaStreamWaitEvent(st, m->enc_join, 0));
     }
     return 0;
 }
@@ -485,9 +555,19 @@ int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
         B2_TRY(rmsnorm_bf16(m->x.p, h, m->final_norm.p, m->xn.p, B, h, d.rms_eps, st));
         B2_TRY(gemm(m->xn.p, h, m->lm_head.p, h, nullptr, nullptr, 0, m->logits.p, V, 1, B, V, h, ACT_NONE, st));
     }
+    {   // A/B switch for measurements: the round-1 tail (argmax + store_token + 2 x add_i32), greedy only, no host ring
+        const char* e = getenv("B2_SAMPLE_LEGACY");
+        if (e != nullptr && e[0] == '1' && kv->samp_host.do_sample == 0 && kv->samp_host.tag == 0 && kv->samp_host.per_row == 0) {
+            B2_TRY(argmax_f32(m->logits.as<float>(), B, V, kv->tok.as<int32_t>(), st));
+            B2_TRY(store_token(kv->tok.as<int32_t>(), kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), B, st));
+            B2_TRY(add_i32(kv->step_counter.as<int32_t>(), 1, 1, st));
+            B2_TRY(add_i32(kv->len_dev.as<int32_t>(), B, 1, st));
+            return 0;
+        }
+    }
     // argmax or temperature/top-k/top-p draw (device-resident SampleState), token feedback, host-ring publication and the
     // step / cache-length counters in ONE launch (was: argmax + store_token + 2 x add_i32)
-    B2_TRY(sample_publish(m->logits.as<float>(), V, B, kv->sstate.as<SampleState>(), kv->tok.as<int32_t>(),
+    B2_TRY(sample_publish(m->logits.as<float>(), V, B, kv->sstate.as<SampleState>(), kv->rows_dev.as<RowState>(), kv->tok.as<int32_t>(),
                           kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), kv->len_dev.as<int32_t>(),
                           kv->ring_dev, kv->ring_cap, SP_SELECT | SP_WRITE_OUT | SP_BUMP, 0, st));
     return 0;
@@ -549,8 +629,9 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     p.scale_log2 = (1.0f / sqrtf((float)m->hd)) * 1.4426950408889634f;
     // greedy streaming: the kernel's fused argmax publishes to the host ring itself; with do_sample the sample_publish
     // launch below overrides the fused argmax (token feedback, out_tokens slot) and publishes instead
-    const bool sampling = kv->samp_host.do_sample != 0;
+    const bool sampling = kv->samp_host.do_sample != 0 || kv->samp_host.per_row != 0;
     if (!sampling && kv->samp_host.tag != 0) { p.sstate = kv->sstate.as<SampleState>(); p.ring = kv->ring_dev; p.ring_cap = kv->ring_cap; }
+    if (kv->samp_host.per_row) p.rows = kv->rows_dev.as<RowState>();
     {   // tuning knobs, re-read every launch so a sweep can flip them inside one process (scripts/mega_sweep.py)
         const char* e = getenv("B2_MEGA_L2_AHEAD");
         int ahead = e ? atoi(e) : kMegaL2AheadDefault;
@@ -588,7 +669,7 @@ int decode_step_mega(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     }
     B2_TRY(decode_mega(p, st));
     if (sampling)
-        B2_TRY(sample_publish(m->logits.as<float>(), d.vocab, B, kv->sstate.as<SampleState>(), kv->tok.as<int32_t>(),
+        B2_TRY(sample_publish(m->logits.as<float>(), d.vocab, B, kv->sstate.as<SampleState>(), kv->rows_dev.as<RowState>(), kv->tok.as<int32_t>(),
                               kv->out_tokens.as<int32_t>(), kv->step_counter.as<int32_t>(), kv->len_dev.as<int32_t>(),
                               kv->ring_dev, kv->ring_cap, SP_SELECT | SP_WRITE_OUT, -1, st));
     return 0;
@@ -815,6 +896,11 @@ int b2_model_finalize(b2_model* m) {
     B2_TRY(m->v_mlp.alloc(vrows * I * 2));
     B2_TRY(m->v_feats.alloc(prow * D * 2));
     B2_TRY(m->p_mid.alloc(prow * h * 2));
+    B2_TRY(m->p_done.alloc(((prow + 127) / 128 + 1) * sizeof(int)));
+    B2_TRY(m->enc_pixels.alloc((size_t)d.max_images * 3 * d.image_size * d.image_size * 2));
+    B2_TRY(m->enc_out.alloc(prow * h * 2));
+    m->enc_graph.assign(d.max_images + 1, nullptr);
+    m->enc_warm.assign(d.max_images + 1, 0);
     const size_t rows = (size_t)d.max_batch * d.max_seq;
     B2_TRY(m->x.alloc(rows * h * 2));
     B2_TRY(m->xn.alloc(rows * h * 2));
@@ -822,6 +908,7 @@ int b2_model_finalize(b2_model* m) {
     B2_TRY(m->attn.alloc(rows * h * 2));
     B2_TRY(m->act.alloc(rows * d.inter * 2));
     B2_TRY(m->last_idx.alloc((size_t)d.max_batch * 4));
+    B2_TRY(m->splice_idx.alloc(rows * 4));
     B2_TRY(m->xlast.alloc((size_t)d.max_batch * h * 2));
     B2_TRY(m->logits.alloc((size_t)d.max_batch * d.vocab * 4));
     m->finalized = true;
@@ -834,10 +921,14 @@ int b2_model_destroy(b2_model* m) {
     cudaDeviceSynchronize();
     if (m->err_host) cudaFreeHost(m->err_host);
     if (m->ws_event) cudaEventDestroy(m->ws_event);
+    for (cudaGraphExec_t g : m->enc_graph) if (g) cudaGraphExecDestroy(g);
+    if (m->enc_stream) cudaStreamDestroy(m->enc_stream);
+    if (m->enc_fork) cudaEventDestroy(m->enc_fork);
+    if (m->enc_join) cudaEventDestroy(m->enc_join);
     DevBuf* top[] = {&m->patch_w, &m->cls, &m->pos, &m->pre_g, &m->pre_b, &m->p0_w, &m->p0_b, &m->p2_w, &m->p2_b,
                      &m->embed, &m->final_norm, &m->lm_head, &m->v_col, &m->v_patch, &m->v_hidden, &m->v_xn,
-                     &m->v_qkv, &m->v_attn, &m->v_mlp, &m->v_feats, &m->p_mid, &m->x, &m->xn, &m->qkv, &m->attn,
-                     &m->act, &m->last_idx, &m->xlast, &m->logits, &m->lm_head8, &m->s_head, &m->xq8, &m->xscale};
+                     &m->v_qkv, &m->v_attn, &m->v_mlp, &m->v_feats, &m->p_mid, &m->p_done, &m->enc_pixels, &m->enc_out, &m->x, &m->xn, &m->qkv, &m->attn,
+                     &m->act, &m->last_idx, &m->xlast, &m->logits, &m->splice_idx, &m->lm_head8, &m->s_head, &m->xq8, &m->xscale};
     for (DevBuf* b : top) b->free();
     for (VitLayer& L : m->vit) {
         DevBuf* bs[12] = {&L.ln1_g, &L.ln1_b, &L.wqkv, &L.bqkv, &L.wo, &L.bo, &L.ln2_g, &L.ln2_b, &L.w1, &L.b1, &L.w2, &L.b2};
@@ -943,8 +1034,13 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
         cudaMemset(kv->sk_counters.p, 0, gemm_skinny_counter_bytes(nmax));
     }
     kv->ring_cap = max_seq;
-    if ((r = kv->sstate.alloc(sizeof(SampleState))) != 0) { b2_kv_destroy(kv); return r; }
+    if ((r = kv->sstate.alloc(sizeof(SampleState))) != 0 || (r = kv->rows_dev.alloc((size_t)max_batch * sizeof(RowState))) != 0) {
+        b2_kv_destroy(kv);
+        return r;
+    }
     cudaMemset(kv->sstate.p, 0, sizeof(SampleState));
+    cudaMemset(kv->rows_dev.p, 0, (size_t)max_batch * sizeof(RowState));
+    kv->rows_host.assign(max_batch, RowState{});
     if (cudaHostAlloc(reinterpret_cast<void**>(&kv->ring_host), (size_t)kv->ring_cap * max_batch * 4, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&kv->ring_dev), kv->ring_host, 0) != cudaSuccess) {
         set_error("b2_kv_create: cannot allocate the pinned token ring (%d x %d)", kv->ring_cap, max_batch);
@@ -985,7 +1081,7 @@ int b2_kv_destroy(b2_kv* kv) {
     if (kv->ev_fork) cudaEventDestroy(kv->ev_fork);
     if (kv->ev_join) cudaEventDestroy(kv->ev_join);
     DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
-                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters, &kv->sstate};
+                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters, &kv->sstate, &kv->rows_dev};
     for (DevBuf* b : bs) b->free();
     delete kv;
     return 0;
@@ -1035,8 +1131,7 @@ int b2_encode_images(b2_model* m, const void* pixels, int B, void* out, void* st
     const size_t img_elems = (size_t)3 * m->d.image_size * m->d.image_size;
     for (int b0 = 0; b0 < B; b0 += m->d.max_images) {
         const int n = B - b0 < m->d.max_images ? B - b0 : m->d.max_images;
-        B2_TRY(vit_forward_chunk(m, reinterpret_cast<const bf16*>(pixels) + b0 * img_elems, n, m->v_feats.p, st));
-        B2_TRY(project_rows(m, m->v_feats.p, n * m->P,
+        B2_TRY(encode_chunk(m, reinterpret_cast<const bf16*>(pixels) + b0 * img_elems, n,
                             reinterpret_cast<bf16*>(out) + (size_t)b0 * m->P * m->d.hidden, st));
     }
     return ws_leave(m, st);
@@ -1051,6 +1146,24 @@ int b2_splice(b2_model* m, const int32_t* src_index, const void* image_feats, in
     DeviceGuard dg(m->device);
     return splice_embed(src_index, m->embed.p, image_feats, embeds_out, rows, m->d.hidden, m->d.vocab, n_feat_rows,
                         m->err_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_splice_ids(b2_model* m, const int64_t* input_ids, int B, int Lt, int k_per_row, const int32_t* feat_offsets_host, int n_img,
+                  const void* image_feats, int S, void* embeds_out, void* stream) {
+    B2_CHECK_ARG(m && input_ids && feat_offsets_host && embeds_out, "b2_splice_ids: null argument");
+    B2_CHECK_ARG(m->finalized, "b2_splice_ids: model not finalized");
+    B2_CHECK_ARG(B >= 1 && S >= 1 && (size_t)B * S <= (size_t)m->d.max_batch * m->d.max_seq,
+                 "b2_splice_ids: B*S=%d exceeds the workspace (%d rows)", B * S, m->d.max_batch * m->d.max_seq);
+    B2_CHECK_ARG(image_feats != nullptr || n_img == 0, "b2_splice_ids: image slots without image_feats");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(ws_enter(m, st));
+    B2_TRY(splice_index(reinterpret_cast<const long long*>(input_ids), B, Lt, k_per_row, feat_offsets_host, n_img, -200, S,
+                        m->splice_idx.as<int32_t>(), m->err_dev, st));
+    B2_TRY(splice_embed(m->splice_idx.as<int32_t>(), m->embed.p, image_feats, embeds_out, B * S, m->d.hidden, m->d.vocab,
+                        n_img > 0 ? feat_offsets_host[n_img] : 0, m->err_dev, st));
+    return ws_leave(m, st);
 }
 
 int b2_async_error(b2_model* m, int* code_out) {
@@ -1072,10 +1185,15 @@ int b2_async_error(b2_model* m, int* code_out) {
 
 int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_lens_host, int B, int S,
                void* logits_out, int logits_mode, void* stream) {
+    return b2_prefill_slots(m, kv, embeds, seq_lens_host, B, S, 0, logits_out, logits_mode, stream);
+}
+
+int b2_prefill_slots(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_lens_host, int B, int S, int slot0,
+                     void* logits_out, int logits_mode, void* stream) {
     B2_CHECK_ARG(m && kv && embeds && kv->m == m, "b2_prefill: bad handle");
     B2_CHECK_ARG(m->finalized, "b2_prefill: model not finalized");
-    B2_CHECK_ARG(B >= 1 && B <= kv->max_batch && S >= 1 && S <= kv->max_seq,
-                 "b2_prefill: B=%d S=%d exceed the KV cache (max_batch=%d max_seq=%d)", B, S, kv->max_batch, kv->max_seq);
+    B2_CHECK_ARG(B >= 1 && slot0 >= 0 && slot0 + B <= kv->max_batch && S >= 1 && S <= kv->max_seq,
+                 "b2_prefill: B=%d S=%d slot0=%d exceed the KV cache (max_batch=%d max_seq=%d)", B, S, slot0, kv->max_batch, kv->max_seq);
     B2_CHECK_ARG((size_t)B * S <= (size_t)m->d.max_batch * m->d.max_seq,
                  "b2_prefill: B*S=%d exceeds the workspace (%d rows)", B * S, m->d.max_batch * m->d.max_seq);
     B2_CHECK_ARG(logits_mode == B2_LOGITS_NONE || logits_out != nullptr, "b2_prefill: logits_out is null");
@@ -1093,14 +1211,15 @@ int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_le
     }
     B2_TRY(ws_enter(m, st));
     // lengths / last-row indices travel as kernel parameters: no pinned staging, no stream sync in this call
-    B2_TRY(set_i32_pairs(kv->len_dev.as<int32_t>(), lens.data(), m->last_idx.as<int32_t>(), last.data(), B, st));
-    for (int b = 0; b < B; ++b) kv->len_host[b] = lens[b];
+    B2_TRY(set_i32_pairs(kv->len_dev.as<int32_t>() + slot0, lens.data(), m->last_idx.as<int32_t>(), last.data(), B, st));
+    for (int b = 0; b < B; ++b) kv->len_host[slot0 + b] = lens[b];
+    const size_t slot_off = (size_t)slot0 * H * kv->max_seq * m->hd;  // cache slabs of the first slot this call fills
 
     B2_CUDA_CHECK(cudaMemcpyAsync(m->x.p, embeds, (size_t)T * h * 2, cudaMemcpyDeviceToDevice, st));
     for (int l = 0; l < d.layers; ++l) {
         LlamaLayer& L = m->ll[l];
-        bf16* kc = kv->k.as<bf16>() + (size_t)l * kv->layer_stride();
-        bf16* vc = kv->v.as<bf16>() + (size_t)l * kv->layer_stride();
+        bf16* kc = kv->k.as<bf16>() + (size_t)l * kv->layer_stride() + slot_off;
+        bf16* vc = kv->v.as<bf16>() + (size_t)l * kv->layer_stride() + slot_off;
         B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln1.p, m->xn.p, T, h, d.rms_eps, st));
         B2_TRY(gemm(m->xn.p, h, L.wqkv.p, h, nullptr, nullptr, 0, m->qkv.p, 3 * h, 0, T, 3 * h, h, ACT_NONE, st));
         B2_TRY(rope_kv_write(m->qkv.p, kc, vc, B, S, H, m->hd, kv->max_seq, d.rope_theta, st));
@@ -1109,7 +1228,7 @@ int b2_prefill(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* seq_le
         fa.k = kc; fa.k_bs = (int64_t)H * kv->max_seq * m->hd; fa.k_ts = m->hd; fa.k_hs = (int64_t)kv->max_seq * m->hd;
         fa.v = vc; fa.v_bs = fa.k_bs; fa.v_ts = m->hd; fa.v_hs = fa.k_hs;
         fa.o = m->attn.p; fa.o_bs = (int64_t)S * h; fa.o_ts = h; fa.o_hs = m->hd;
-        fa.seq_lens = kv->len_dev.as<int32_t>();
+        fa.seq_lens = kv->len_dev.as<int32_t>() + slot0;
         fa.B = B; fa.H = H; fa.S = S; fa.D = m->hd; fa.causal = 1;
         fa.scale = 1.0f / sqrtf((float)m->hd);
         B2_TRY(flash_attn_bf16(fa, st));
@@ -1141,7 +1260,7 @@ static int copy_tokens_in(b2_kv* kv, const int32_t* tokens, int B, cudaStream_t 
 static int set_sampling(b2_kv* kv, const SampleState& v, bool force, cudaStream_t st) {
     const SampleState& c = kv->samp_host;
     if (!force && kv->samp_valid && c.do_sample == v.do_sample && c.temperature == v.temperature && c.top_p == v.top_p &&
-        c.top_k == v.top_k && c.seed == v.seed && c.tag == v.tag)
+        c.top_k == v.top_k && c.seed == v.seed && c.tag == v.tag && c.per_row == v.per_row)
         return 0;
     B2_TRY(sample_state_set(kv->sstate.as<SampleState>(), v, st));
     kv->samp_host = v;
@@ -1244,7 +1363,7 @@ int b2_stream_begin(b2_model* m, b2_kv* kv, const float* logits, int B, const b2
     B2_TRY(set_sampling(kv, v, true, st));
     B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
     // token 0: chosen from the prefill's last-position logits, published as ring entry 0, fed to the first decode step
-    B2_TRY(sample_publish(logits, m->d.vocab, B, kv->sstate.as<SampleState>(), kv->tok.as<int32_t>(), nullptr,
+    B2_TRY(sample_publish(logits, m->d.vocab, B, kv->sstate.as<SampleState>(), kv->rows_dev.as<RowState>(), kv->tok.as<int32_t>(), nullptr,
                           kv->step_counter.as<int32_t>(), kv->len_dev.as<int32_t>(), kv->ring_dev, kv->ring_cap, SP_SELECT, 0, st));
     kv->stream_B = B; kv->stream_tag = v.tag; kv->stream_scheduled = 1;
     return ws_leave(m, st);
@@ -1256,19 +1375,67 @@ int b2_stream_enqueue(b2_model* m, b2_kv* kv, int n_steps, void* stream) {
     DeviceGuard dg(m->device);
     B2_CHECK_ARG(kv->stream_B >= 1, "b2_stream_enqueue: no streaming generation on this cache (b2_stream_begin first)");
     const int B = kv->stream_B;
-    B2_CHECK_ARG(kv->stream_scheduled + n_steps <= kv->ring_cap, "b2_stream_enqueue: %d tokens exceed the ring capacity %d",
+    const bool per_row = kv->samp_host.per_row != 0;
+    // one generation never outgrows the ring (ring_cap = max_seq); a continuously batched cache runs indefinitely and wraps
+    B2_CHECK_ARG(per_row || kv->stream_scheduled + n_steps <= kv->ring_cap, "b2_stream_enqueue: %d tokens exceed the ring capacity %d",
                  kv->stream_scheduled + n_steps, kv->ring_cap);
     for (int b = 0; b < B; ++b)
-        B2_CHECK_ARG(kv->len_host[b] + n_steps <= kv->max_seq, "b2_stream_enqueue: sample %d cache length %d + %d steps exceeds capacity %d",
-                     b, kv->len_host[b], n_steps, kv->max_seq);
+        B2_CHECK_ARG((per_row && !kv->rows_host[b].active) || kv->len_host[b] + n_steps <= kv->max_seq,
+                     "b2_stream_enqueue: sample %d cache length %d + %d steps exceeds capacity %d", b, kv->len_host[b], n_steps, kv->max_seq);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     B2_TRY(ws_enter(m, st));
     cudaStream_t run = nullptr;
     B2_TRY(fork_stream(kv, st, &run));
     for (int s = 0; s < n_steps; ++s) B2_TRY(decode_step_run(m, kv, B, run));
     B2_TRY(join_stream(kv, st, run));
-    for (int b = 0; b < B; ++b) kv->len_host[b] += n_steps;
+    for (int b = 0; b < B; ++b)
+        if (!per_row || kv->rows_host[b].active) kv->len_host[b] += n_steps;
     kv->stream_scheduled += n_steps;
+    return ws_leave(m, st);
+}
+
+// ---- continuous batching: requests join and leave the slots of one cache between decode steps ----------------------------
+int b2_batch_begin(b2_model* m, b2_kv* kv, int B, void* stream) {
+    B2_CHECK_ARG(m && kv && kv->m == m && B >= 1 && B <= kv->max_batch, "b2_batch_begin: bad argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SampleState v = {};
+    v.temperature = 1.f; v.top_p = 1.f; v.per_row = 1;
+    kv->epoch += 1;
+    v.tag = 1 + kv->epoch % 2047;
+    B2_TRY(ws_enter(m, st));
+    B2_TRY(set_sampling(kv, v, true, st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->step_counter.p, 0, 4, st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->rows_dev.p, 0, (size_t)kv->max_batch * sizeof(RowState), st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->len_dev.p, 0, (size_t)kv->max_batch * 4, st));
+    B2_CUDA_CHECK(cudaMemsetAsync(kv->tok.p, 0, (size_t)kv->max_batch * 4, st));
+    kv->rows_host.assign(kv->max_batch, RowState{});
+    kv->len_host.assign(kv->max_batch, 0);
+    kv->stream_B = B; kv->stream_tag = v.tag; kv->stream_scheduled = 0;
+    return ws_leave(m, st);
+}
+
+int b2_batch_set_row(b2_model* m, b2_kv* kv, int slot, int active, const b2_sampling* sp, int first_token, void* stream) {
+    B2_CHECK_ARG(m && kv && kv->m == m && slot >= 0 && slot < kv->stream_B, "b2_batch_set_row: bad slot %d", slot);
+    B2_CHECK_ARG(kv->samp_host.per_row != 0, "b2_batch_set_row: b2_batch_begin first");
+    RowState v = {};
+    v.active = active ? 1 : 0; v.temperature = 1.f; v.top_p = 1.f; v.index = 1;  // draw 0 chose first_token
+    if (active && sp != nullptr && sp->do_sample) {
+        B2_CHECK_ARG(sp->temperature > 0.f && sp->top_p > 0.f && sp->top_p <= 1.f && sp->top_k >= 0, "b2_batch_set_row: bad sampling parameters");
+        v.do_sample = 1; v.temperature = sp->temperature; v.top_p = sp->top_p; v.top_k = sp->top_k; v.seed = sp->seed;
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard dg(m->device);
+    B2_CHECK_ARG(!active || kv->len_host[slot] >= 1, "b2_batch_set_row: slot %d has an empty cache (prefill it first)", slot);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B2_TRY(ws_enter(m, st));
+    B2_TRY(row_state_set(kv->rows_dev.as<RowState>() + slot, v, active ? kv->tok.as<int32_t>() + slot : nullptr, first_token, st));
+    if (!active) {  // a freed slot restarts from an empty cache
+        B2_CUDA_CHECK(cudaMemsetAsync(kv->len_dev.as<int32_t>() + slot, 0, 4, st));
+        kv->len_host[slot] = 0;
+    }
+    kv->rows_host[slot] = v;
     return ws_leave(m, st);
 }
 
@@ -1276,11 +1443,12 @@ int b2_stream_enqueue(b2_model* m, b2_kv* kv, int n_steps, void* stream) {
 // Takes no lock: other threads keep issuing work on the model while this one waits.
 int b2_stream_wait(b2_kv* kv, int index, int32_t* tokens_host, int timeout_ms) {
     B2_CHECK_ARG(kv && tokens_host && index >= 0, "b2_stream_wait: bad argument");
-    const int B = kv->stream_B, tag = kv->stream_tag;
+    const int B = kv->stream_B;
     B2_CHECK_ARG(B >= 1, "b2_stream_wait: no streaming generation on this cache");
     B2_CHECK_ARG(index < kv->stream_scheduled, "b2_stream_wait: token %d has not been scheduled (%d scheduled)", index,
                  kv->stream_scheduled);
     volatile int32_t* slot = kv->ring_host + (size_t)(index % kv->ring_cap) * B;
+    const int tag = 1 + (kv->stream_tag - 1 + index / kv->ring_cap) % 2047;  // the tag advances when the ring wraps (sampling.cu)
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (unsigned long long spins = 0;; ++spins) {
@@ -1304,6 +1472,18 @@ int b2_stream_wait(b2_kv* kv, int index, int32_t* tokens_host, int timeout_ms) {
     }
 }
 
+int b2_op_preprocess_clip(const b2_preprocess_plan* pl, void* stream) {
+    B2_CHECK_ARG(pl != nullptr, "b2_op_preprocess_clip: null plan");
+    PreprocessArgs a;
+    a.img = pl->img; a.H = pl->H; a.W = pl->W; a.pad_top = pl->pad_top; a.pad_left = pl->pad_left;
+    for (int i = 0; i < 3; ++i) { a.bg[i] = pl->bg[i]; a.mean[i] = pl->mean[i]; a.stdv[i] = pl->stdv[i]; }
+    a.h_bounds = pl->h_bounds; a.h_kk = pl->h_kk; a.h_ksize = pl->h_ksize; a.h_identity = pl->h_identity;
+    a.v_bounds = pl->v_bounds; a.v_kk = pl->v_kk; a.v_ksize = pl->v_ksize; a.v_identity = pl->v_identity;
+    a.y0 = pl->y0; a.rows = pl->rows; a.x_lo = pl->x_lo; a.y_lo = pl->y_lo; a.cols = pl->out; a.out = pl->out;
+    a.tmp = pl->tmp; a.rescale = pl->rescale; a.pixels = pl->pixels; a.u8_out = pl->u8_out;
+    return preprocess_clip_image(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // standalone selection (unit tests, first-token choice outside a streaming generation): out_tokens[b] (device int32)
 int b2_op_sample(const float* logits, int B, int V, const b2_sampling* sp, int index, int32_t* out_tokens, void* stream) {
     B2_CHECK_ARG(logits && out_tokens && B >= 1 && V >= 1 && index >= 0, "b2_op_sample: bad argument");
@@ -1319,7 +1499,7 @@ int b2_op_sample(const float* logits, int B, int V, const b2_sampling* sp, int i
     B2_TRY(tmp.alloc(sizeof(SampleState) + 64));
     int r = sample_state_set(tmp.as<SampleState>(), v, st);
     if (r == 0)
-        r = sample_publish(logits, V, B, tmp.as<SampleState>(), out_tokens, nullptr, nullptr, nullptr, nullptr, 0, SP_SELECT, 0, st);
+        r = sample_publish(logits, V, B, tmp.as<SampleState>(), nullptr, out_tokens, nullptr, nullptr, nullptr, nullptr, 0, SP_SELECT, 0, st);
     cudaError_t e = cudaStreamSynchronize(st);
     tmp.free();
     if (r != 0) return r;

@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t radix_select(const float* s_x, int V, unsign
 }
 
 __global__ void __launch_bounds__(SP_THREADS, 1)
-sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleState* st, int32_t* tok, int32_t* out_tokens,
+sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleState* st, RowState* rows, int32_t* tok, int32_t* out_tokens,
                       int32_t* step_counter, int32_t* cur_len, volatile int32_t* ring, int ring_cap, int flags,
                       int step_offset) {
     extern __shared__ __align__(16) uint8_t sp_smem[];
@@ -154,21 +154,30 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
     __shared__ int s_choice;
 
     const int tid = threadIdx.x, b = blockIdx.x;
-    const int do_sample = st->do_sample;
+    const bool per_row = st->per_row != 0;
+    const bool active = !per_row || rows[b].active != 0;
+    const int do_sample = per_row ? rows[b].do_sample : st->do_sample;
+    const float temperature = per_row ? rows[b].temperature : st->temperature;
+    const float top_p = per_row ? rows[b].top_p : st->top_p;
+    const int top_k = per_row ? rows[b].top_k : st->top_k;
+    const unsigned long long seed = per_row ? rows[b].seed : st->seed;
     const int pub = st->pub_counter;
+    const int draw = per_row ? rows[b].index : pub;
     int choice = 0;
 
-    if (!(flags & SP_SELECT)) {
+    if (!active) {
+        choice = tok[b];  // an idle slot keeps its token; nothing is selected or counted for it
+    } else if (!(flags & SP_SELECT)) {
         choice = tok[b];  // already chosen by the producer of `tok` (decode megakernel's fused argmax)
     } else if (!do_sample) {
         choice = block_argmax(logits + (size_t)b * V, V, tid, s_v, s_i, nullptr);
     } else {
         const float* row = logits + (size_t)b * V;
-        const float inv_t = 1.0f / st->temperature;
+        const float inv_t = 1.0f / temperature;
         for (int i = tid; i < V; i += SP_THREADS) s_x[i] = row[i] * inv_t;
         __syncthreads();
         // ---- top-k: keep everything >= the k-th largest scaled logit (ties kept, like TopKLogitsWarper) ----
-        const int k = st->top_k;
+        const int k = top_k;
         if (k > 0 && k < V) {
             const uint32_t kth = radix_select<false>(s_x, V, (unsigned long long)k, tid, s_hist, &s_prefix, &s_above);
             for (int i = tid; i < V; i += SP_THREADS)
@@ -184,7 +193,6 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
         }
         __syncthreads();
         // ---- top-p over the fixed-point masses ----
-        const float top_p = st->top_p;
         if (top_p < 1.0f) {
             unsigned long long part = 0ull;
             for (int i = tid; i < V; i += SP_THREADS) part += mass_of(s_x[i]);
@@ -219,7 +227,7 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
         }
         const unsigned long long excl = warp_base + incl - mine;
         if (tid == 0) {
-            s_target = total ? __umul64hi(total, philox_u64(st->seed, (uint32_t)pub, (uint32_t)b)) : 0ull;
+            s_target = total ? __umul64hi(total, philox_u64(seed, (uint32_t)draw, (uint32_t)b)) : 0ull;
             s_choice = 0;
         }
         __syncthreads();
@@ -239,10 +247,13 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
     }
 
     if (tid == 0) {
-        if (flags & SP_SELECT) tok[b] = choice;
+        if ((flags & SP_SELECT) && active) tok[b] = choice;
+        if (per_row && active) rows[b].index = draw + 1;
         if (flags & SP_WRITE_OUT) out_tokens[(size_t)(*step_counter + step_offset) * B + b] = choice;
-        if (ring != nullptr) {
-            ring[(size_t)(pub % ring_cap) * B + b] = (st->tag << 20) | (choice & 0xFFFFF);
+        if (ring != nullptr && st->tag != 0) {
+            // the tag advances every time the ring wraps, so an entry left from ring_cap steps ago is never taken for a new one
+            const int tag = 1 + (st->tag - 1 + pub / ring_cap) % 2047;
+            ring[(size_t)(pub % ring_cap) * B + b] = (tag << 20) | (choice & 0xFFFFF);
             __threadfence_system();
         }
         __threadfence();
@@ -251,7 +262,8 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
             st->pub_counter = pub + 1;
             if (flags & SP_BUMP) {
                 *step_counter += 1;
-                for (int i = 0; i < B; ++i) cur_len[i] += 1;
+                for (int i = 0; i < B; ++i)
+                    if (!per_row || rows[i].active) cur_len[i] += 1;
             }
         }
     }
@@ -259,6 +271,12 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
 
 __global__ void sample_state_set_kernel(SampleState* st, SampleState v) {
     if (threadIdx.x == 0) *st = v;
+}
+__global__ void row_state_set_kernel(RowState* row, RowState v, int32_t* tok, int token) {
+    if (threadIdx.x == 0) {
+        *row = v;
+        if (tok != nullptr) *tok = token;
+    }
 }
 
 }  // namespace
@@ -271,7 +289,13 @@ int sample_state_set(SampleState* st_dev, const SampleState& v, cudaStream_t str
     return 0;
 }
 
-int sample_publish(const float* logits, int V, int B, SampleState* st_dev, int32_t* tok, int32_t* out_tokens,
+int row_state_set(RowState* row_dev, const RowState& v, int32_t* tok_dev, int token, cudaStream_t stream) {
+    row_state_set_kernel<<<1, 32, 0, stream>>>(row_dev, v, tok_dev, token);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int sample_publish(const float* logits, int V, int B, SampleState* st_dev, RowState* rows_dev, int32_t* tok, int32_t* out_tokens,
                    int32_t* step_counter, int32_t* cur_len, int32_t* ring_dev, int ring_cap, int flags, int step_offset,
                    cudaStream_t stream) {
     B2_CHECK_ARG(B >= 1 && V >= 1 && st_dev != nullptr && tok != nullptr, "sample_publish: bad argument");
@@ -283,7 +307,7 @@ int sample_publish(const float* logits, int V, int B, SampleState* st_dev, int32
         B2_CUDA_CHECK(cudaFuncSetAttribute(sample_publish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    sample_publish_kernel<<<B, SP_THREADS, smem, stream>>>(logits, V, B, st_dev, tok, out_tokens, step_counter, cur_len,
+    sample_publish_kernel<<<B, SP_THREADS, smem, stream>>>(logits, V, B, st_dev, rows_dev, tok, out_tokens, step_counter, cur_len,
                                                            ring_dev, ring_cap, flags, step_offset);
     B2_LAUNCH_CHECK();
     return 0;

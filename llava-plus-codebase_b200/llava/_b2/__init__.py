@@ -20,6 +20,7 @@ DT_BF16, DT_F16, DT_F32 = 0, 1, 2
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_SWIGLU = 0, 1, 2, 3
 LOGITS_NONE, LOGITS_LAST, LOGITS_ALL = 0, 1, 2
 INT32_MIN = -(2**31)
+ERR_TOKEN_RANGE, ERR_IMAGE_ROW_RANGE, ERR_SPLICE_SLOTS = 1, 2, 4
 
 _c = ctypes
 _vp, _i32, _i64, _f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
@@ -40,6 +41,16 @@ class Sampling(_c.Structure):
     """b2_sampling (include/b2llava.h): do_sample == 0 -> greedy argmax."""
     _fields_ = [("do_sample", _c.c_int32), ("temperature", _c.c_float), ("top_p", _c.c_float),
                 ("top_k", _c.c_int32), ("seed", _c.c_ulonglong)]
+
+
+class PreprocessPlan(_c.Structure):
+    """b2_preprocess_plan (include/b2llava.h)."""
+    _fields_ = [("img", _vp), ("H", _c.c_int32), ("W", _c.c_int32), ("pad_top", _c.c_int32), ("pad_left", _c.c_int32),
+                ("bg", _c.c_uint8 * 4), ("h_bounds", _vp), ("h_kk", _vp), ("h_ksize", _c.c_int32), ("h_identity", _c.c_int32),
+                ("v_bounds", _vp), ("v_kk", _vp), ("v_ksize", _c.c_int32), ("v_identity", _c.c_int32),
+                ("y0", _c.c_int32), ("rows", _c.c_int32), ("x_lo", _c.c_int32), ("y_lo", _c.c_int32), ("out", _c.c_int32),
+                ("tmp", _vp), ("mean", _c.c_float * 3), ("stdv", _c.c_float * 3), ("rescale", _c.c_float),
+                ("pixels", _vp), ("u8_out", _vp)]
 
 
 def make_sampling(do_sample=False, temperature=1.0, top_p=1.0, top_k=0, seed=0):
@@ -66,12 +77,17 @@ SIGNATURES = {
     "b2_project": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2_encode_images": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2_splice": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "b2_splice_ids": (_i32, [_vp, _vp, _i32, _i32, _i32, _c.POINTER(_c.c_int32), _i32, _vp, _i32, _vp, _vp]),
     "b2_async_error": (_i32, [_vp, _c.POINTER(_c.c_int)]),
     "b2_stream_begin": (_i32, [_vp, _vp, _vp, _i32, _c.POINTER(Sampling), _vp]),
     "b2_stream_enqueue": (_i32, [_vp, _vp, _i32, _vp]),
     "b2_stream_wait": (_i32, [_vp, _i32, _c.POINTER(_c.c_int32), _i32]),
+    "b2_op_preprocess_clip": (_i32, [_c.POINTER(PreprocessPlan), _vp]),
     "b2_op_sample": (_i32, [_vp, _i32, _i32, _c.POINTER(Sampling), _i32, _vp, _vp]),
     "b2_prefill": (_i32, [_vp, _vp, _vp, _c.POINTER(_c.c_int32), _i32, _i32, _vp, _i32, _vp]),
+    "b2_prefill_slots": (_i32, [_vp, _vp, _vp, _c.POINTER(_c.c_int32), _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_batch_begin": (_i32, [_vp, _vp, _i32, _vp]),
+    "b2_batch_set_row": (_i32, [_vp, _vp, _i32, _i32, _c.POINTER(Sampling), _i32, _vp]),
     "b2_decode_step": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b2_decode_greedy": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2_argmax": (_i32, [_vp, _i32, _i32, _vp, _vp]),
@@ -278,15 +294,38 @@ class Engine:
                   "b2_splice")
         return out
 
+    def splice_ids(self, input_ids, k_per_row, feat_rows, image_feats):
+        """Device-side splice for equal-length unpadded rows: input_ids int64 [B, Lt] ON THE DEVICE, k_per_row image
+        placeholders per row, feat_rows[j] = feature rows of image slot j (row-major slot order). Returns embeds
+        [B, S, hidden] with S = Lt - k + sum(feat rows of one row) and no host synchronisation. A wrong placeholder count is
+        reported by take_async_error() (ERR_SPLICE_SLOTS) once the stream has run."""
+        B, Lt = input_ids.shape
+        n_img = len(feat_rows)
+        assert n_img == B * k_per_row and input_ids.dtype == torch.int64 and input_ids.is_cuda and input_ids.is_contiguous()
+        per_row = [sum(feat_rows[b * k_per_row:(b + 1) * k_per_row]) for b in range(B)]
+        assert len(set(per_row)) == 1, "rows must receive the same number of feature rows"
+        S = Lt - k_per_row + per_row[0]
+        off = (_c.c_int32 * (n_img + 1))(*([0] + [sum(feat_rows[:j + 1]) for j in range(n_img)]))
+        out = torch.empty(B, S, self.hidden, dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_splice_ids(self.handle, ptr(input_ids), B, Lt, int(k_per_row), off, n_img, ptr(image_feats), S,
+                                         ptr(out), stream_ptr()), "b2_splice_ids")
+        return out
+
+    def take_async_error(self):
+        """Bit mask of the input problems kernels have flagged since the last call (ERR_* below); clears it."""
+        code = _c.c_int(0)
+        check(self.lib.b2_async_error(self.handle, ctypes.byref(code)), "b2_async_error")
+        return code.value
+
     def check_async_error(self):
         """Raise ValueError if a kernel flagged bad inputs (ids outside the embedding table, image placeholder without
         features). Call after a point where the stream has been synchronised (e.g. once the first token is on the host)."""
-        code = _c.c_int(0)
-        check(self.lib.b2_async_error(self.handle, ctypes.byref(code)), "b2_async_error")
-        if code.value:
+        if self.take_async_error():
             raise ValueError(last_error())
 
-    def prefill(self, kv, embeds, seq_lens=None, logits_mode=LOGITS_LAST):
+    def prefill(self, kv, embeds, seq_lens=None, logits_mode=LOGITS_LAST, slot0=0):
+        """`slot0`: first cache slot to fill (continuous batching); the other slots keep their contents."""
         embeds = self._bf16(embeds)
         B, S = embeds.shape[0], embeds.shape[1]
         lens = None
@@ -298,8 +337,8 @@ class Engine:
         elif logits_mode == LOGITS_ALL:
             logits = torch.empty(B, S, self.vocab, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.index):
-            check(self.lib.b2_prefill(self.handle, kv.handle, ptr(embeds), lens, B, S, ptr(logits), logits_mode,
-                                      stream_ptr()), "b2_prefill")
+            check(self.lib.b2_prefill_slots(self.handle, kv.handle, ptr(embeds), lens, B, S, int(slot0), ptr(logits), logits_mode,
+                                            stream_ptr()), "b2_prefill")
         return logits
 
     def decode_step(self, kv, tokens, want_logits=True):
@@ -332,6 +371,16 @@ class Engine:
         with torch.cuda.device(self.index):
             check(self.lib.b2_stream_begin(self.handle, kv.handle, ptr(logits), int(logits.shape[0]), ctypes.byref(sp),
                                            stream_ptr()), "b2_stream_begin")
+
+    def batch_begin(self, kv, B):
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_batch_begin(self.handle, kv.handle, int(B), stream_ptr()), "b2_batch_begin")
+
+    def batch_set_row(self, kv, slot, active, sampling=None, first_token=0):
+        sp = sampling if sampling is not None else make_sampling()
+        with torch.cuda.device(self.index):
+            check(self.lib.b2_batch_set_row(self.handle, kv.handle, int(slot), int(bool(active)), ctypes.byref(sp), int(first_token),
+                                            stream_ptr()), "b2_batch_set_row")
 
     def stream_enqueue(self, kv, n_steps):
         with torch.cuda.device(self.index):

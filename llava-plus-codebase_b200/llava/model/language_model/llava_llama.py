@@ -24,7 +24,7 @@ from transformers.modeling_outputs import CausalLMOutputWithPast
 
 from ..llava_arch import LlavaMetaModel, LlavaMetaForCausalLM
 from ..multimodal_encoder.clip_encoder import _Holder, _read_checkpoint_dir
-from ..._b2 import Engine, KVCache, LOGITS_ALL, LOGITS_LAST, make_sampling
+from ..._b2 import Engine, KVCache, LOGITS_ALL, LOGITS_LAST, ERR_SPLICE_SLOTS, last_error, make_sampling
 
 
 class LlavaConfig(LlamaConfig):
@@ -143,6 +143,7 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         self.vocab_size = config.vocab_size
         self.lm_head = _Weight(config.vocab_size, config.hidden_size, dtype=dtype, device=device)
         self._engine = None
+        self._batcher = None       # config.b2_continuous_batching = N: concurrent generate() calls share batched decode steps
         self._pool = None          # generate(): one exclusive cache per call
         self._fwd_kvs = []         # forward(use_cache=True): small LRU ring of leased caches
         self._fwd_lock = threading.Lock()
@@ -180,6 +181,9 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
     def invalidate_engine(self):
         """Weights changed (load_state_dict, resize, tower load): rebuild the device engine lazily."""
         with self._engine_lock:
+            if self._batcher is not None:
+                self._batcher.close()
+                self._batcher = None
             self._pool = None
             self._fwd_kvs = []
             if self._engine is not None:
@@ -244,7 +248,8 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             hidden=c.hidden_size, inter=c.intermediate_size, layers=c.num_hidden_layers,
             heads=c.num_attention_heads, vocab=self.lm_head.weight.shape[0], rms_eps=c.rms_norm_eps,
             rope_theta=float(getattr(c, "rope_theta", None) or (getattr(c, "rope_parameters", None) or {}).get("rope_theta", 10000.0)),
-            max_batch=self._limits["max_batch"] or 1, max_seq=max_seq, max_images=self._limits["max_images"] or 8,
+            max_batch=max(self._limits["max_batch"] or 1, int(getattr(c, "b2_continuous_batching", 0) or 0)),
+            max_seq=max_seq, max_images=self._limits["max_images"] or 8,
         )
         if getattr(vc, "hidden_act", "quick_gelu") != "quick_gelu":
             raise NotImplementedError("CLIP tower activation must be quick_gelu (openai/clip-vit-large-patch14-336)")
@@ -263,6 +268,16 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         self._fwd_kvs = []
         self._engine = eng
         return eng
+
+    def _get_batcher(self, eng):
+        slots = int(getattr(self.config, "b2_continuous_batching", 0) or 0)
+        if slots < 2:
+            return None
+        with self._engine_lock:
+            if self._batcher is None:
+                from ..._b2.batching import ContinuousBatcher
+                self._batcher = ContinuousBatcher(eng, slots, eng.desc.max_seq)
+            return self._batcher
 
     def _check_limits(self, eng, B, need_seq):
         lim_b, lim_s = eng.desc.max_batch, eng.desc.max_seq
@@ -432,35 +447,78 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             sampling = make_sampling(True, temperature, 1.0 if top_p is None else top_p, 50 if top_k is None else top_k, seed)
         prof = _StageTimer() if os.environ.get("B2_PROFILE_GENERATE") else None
 
+        batcher = self._get_batcher(engine) if B == 1 else None
+        if batcher is not None:
+            # continuous batching: this thread splices its prompt and runs its own host loop (streamer, eos, criteria); the
+            # decode steps are shared with every other generate() in flight (llava/_b2/batching.py)
+            from ..._b2.batching import RequestStream
+            embeds = lens = None
+            if images is not None and self.get_vision_tower() is not None:
+                embeds, lens, speculative = self._spliced_embeds(prompt, attention_mask, images)
+                if speculative:
+                    torch.cuda.current_stream(engine.device).synchronize()
+                    if engine.take_async_error() & ERR_SPLICE_SLOTS:
+                        embeds, lens, _ = self._spliced_embeds(prompt, attention_mask, images, force_host=True)
+            if embeds is None:
+                embeds = engine.splice(prompt.to(torch.int32).reshape(-1).to(engine.device), None, 1, Lt)
+                lens = [Lt]
+            self._check_limits(engine, 1, lens[0] + max_new_tokens)
+            req = batcher.submit(embeds, lens[0], sampling, max_new_tokens)
+            if streamer is not None:
+                streamer.put(prompt.cpu())
+            pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
+            try:
+                new_tokens = _stream_decode(RequestStream(req), None, None, sampling, 1, max_new_tokens, eos_ids, pad, prompt,
+                                            streamer, stopping_criteria, begun=True)
+            finally:
+                req.cancel()
+            if streamer is not None:
+                streamer.end()
+            return torch.cat([prompt, new_tokens.to(device=prompt.device, dtype=prompt.dtype)], dim=1)
+
         kv = self._pool.acquire()  # exclusive for this call (concurrent generate() threads each get their own)
         try:
-            # ---- prefill: splice + decoder, last-position logits only ----
-            embeds = None
-            if images is not None and self.get_vision_tower() is not None:
-                embeds, lens = self._spliced_embeds(prompt, attention_mask, images)
-            if embeds is not None:
-                if getattr(self.config, "tokenizer_padding_side", "right") == "left" and len(set(lens)) > 1:
-                    S = embeds.shape[1]
-                    embeds = torch.stack([torch.roll(embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
-            else:  # text-only prompt (or a [B,1] prompt, which the multimodal splice passes through)
-                if attention_mask is not None and not bool(attention_mask.bool().all()):
-                    raise NotImplementedError("padded text-only batches: pass equal-length prompts")
-                ids = prompt.to(torch.int32).reshape(-1).to(engine.device)
-                embeds = engine.splice(ids, None, B, Lt)
-                lens = [Lt] * B
-            if prof: prof.mark("encode_images+splice")
-            self._check_limits(engine, B, max(lens) + max_new_tokens)
-            kv.reset()
-            logits = engine.prefill(kv, embeds, lens, LOGITS_LAST)
-            if prof: prof.mark("prefill")
+            # ---- prefill: splice + decoder, last-position logits only; token 0 is chosen on the device ----
+            def prefill(force_host):
+                embeds, lens, speculative = None, None, False
+                if images is not None and self.get_vision_tower() is not None:
+                    embeds, lens, speculative = self._spliced_embeds(prompt, attention_mask, images, force_host=force_host)
+                if embeds is not None:
+                    if getattr(self.config, "tokenizer_padding_side", "right") == "left" and len(set(lens)) > 1:
+                        S = embeds.shape[1]
+                        embeds = torch.stack([torch.roll(embeds[b], shifts=-(S - lens[b]), dims=0) for b in range(B)])
+                else:  # text-only prompt (or a [B,1] prompt, which the multimodal splice passes through)
+                    if attention_mask is not None and not bool(attention_mask.bool().all()):
+                        raise NotImplementedError("padded text-only batches: pass equal-length prompts")
+                    ids = prompt.to(torch.int32).reshape(-1).to(engine.device)
+                    embeds = engine.splice(ids, None, B, Lt)
+                    lens = [Lt] * B
+                if prof: prof.mark("encode_images+splice")
+                self._check_limits(engine, B, max(lens) + max_new_tokens)
+                kv.reset()
+                logits = engine.prefill(kv, embeds, lens, LOGITS_LAST)
+                engine.stream_begin(kv, logits, sampling)
+                engine.stream_wait(kv, 0, B)          # first sync of this call: every input check has run by now
+                if prof: prof.mark("prefill + first token")
+                return speculative
+
+            speculative = prefill(False)
+            err = engine.take_async_error()
+            if speculative and (err & ERR_SPLICE_SLOTS):
+                # the rows do not hold n_images / B placeholders each: the shape-only output length was wrong. Redo on the
+                # host path, which reproduces the reference's behaviour for that input (extra images ignored / IndexError)
+                speculative = prefill(True)
+                err = engine.take_async_error()
+            if err:
+                raise ValueError(last_error())
 
             if streamer is not None:
                 streamer.put(prompt.cpu())
             pad = pad_token_id if pad_token_id is not None else (next(iter(eos_ids)) if eos_ids else 0)
-            new_tokens = _stream_decode(engine, kv, logits, sampling, B, max_new_tokens, eos_ids, pad, prompt,
+            new_tokens = _stream_decode(engine, kv, None, sampling, B, max_new_tokens, eos_ids, pad, prompt,
                                         streamer, stopping_criteria,
-                                        run_ahead=int(getattr(self.config, "b2_run_ahead", 8)))
-            engine.check_async_error()  # the first token has been read: every input check of this call has run
+                                        run_ahead=int(getattr(self.config, "b2_run_ahead", 8)), begun=True)
+            engine.check_async_error()
             if prof: prof.mark("decode")
         finally:
             self._pool.release(kv)
@@ -506,7 +564,7 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
 
 
 def _stream_decode(engine, kv, logits, sampling, B, max_new_tokens, eos_ids, pad, prompt, streamer, stopping_criteria,
-                   run_ahead=8):
+                   run_ahead=8, begun=False):
     """Host half of the decode loop. The device chooses token 0 from the prefill `logits` and then runs up to `run_ahead`
     steps in front of this loop; `engine.stream_wait(kv, t, B)` hands over token t as soon as its kernel has written it
     to pinned memory. Per token, in the order HF's loop uses: finished rows show `pad`; streamer.put; eos bookkeeping;
@@ -518,7 +576,8 @@ def _stream_decode(engine, kv, logits, sampling, B, max_new_tokens, eos_ids, pad
         crit_buf = torch.empty(B, Lt + max_new_tokens, dtype=torch.long)
         crit_buf[:, :Lt] = prompt.to("cpu", torch.long)
     run_ahead = max(1, int(run_ahead))
-    engine.stream_begin(kv, logits, sampling)
+    if not begun:  # generate() begins the stream itself (it confirms its input checks on token 0 before any output)
+        engine.stream_begin(kv, logits, sampling)
     scheduled = 1                                   # tokens whose kernels have been queued (token 0 = begin)
     finished = [False] * B
     cols = []

@@ -164,13 +164,37 @@ class LlavaMetaForCausalLM(ABC):
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images):
         return self._prepare_multimodal(input_ids, position_ids, attention_mask, past_key_values, labels, images)[0]
 
-    def _spliced_embeds(self, input_ids, attention_mask, images):
-        """generate()'s use of the splice: (inputs_embeds [B,S,h], valid length per row), or (None, None) when the
-        multimodal branch passes the ids through (single-token prompts)."""
-        out, lens = self._prepare_multimodal(input_ids, None, attention_mask, None, None, images)
-        return out[4], lens
+    def _spliced_embeds(self, input_ids, attention_mask, images, force_host=False):
+        """generate()'s use of the splice: (inputs_embeds [B,S,h], valid length per row, speculative), or (None, None, False)
+        when the multimodal branch passes the ids through (single-token prompts).
 
-    def _prepare_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images):
+        Ids that already live on the device are spliced THERE (b2_splice_ids: prefix count over `ids == IMAGE_TOKEN_INDEX`, no
+        D2H of the ids, no host loop; the reference syncs per row, llava_arch.py:143-187) for the layout every generation
+        caller uses — equal-length rows, no padding mask, the same number of placeholders per row. The output length then
+        follows from shapes alone, on the assumption that each row holds n_images / B placeholders: `speculative` tells the
+        caller to confirm it (Engine.take_async_error() & ERR_SPLICE_SLOTS after its first sync) and to redo the splice with
+        force_host=True otherwise, which reproduces the reference's exact semantics (extra images ignored, IndexError ...)."""
+        tower = self.get_vision_tower()
+        if (not force_host and tower is not None and images is not None and attention_mask is None and input_ids.is_cuda
+                and input_ids.shape[1] > 1):
+            B, Lt = input_ids.shape
+            image_feats, feats_per_image = self._image_features(images)
+            n_img = len(feats_per_image)
+            k = n_img // B if n_img % B == 0 else 0
+            per_row = {sum(feats_per_image[b * k:(b + 1) * k]) for b in range(B)} if k else set()
+            max_len = getattr(self.config, "tokenizer_model_max_length", None)
+            if k >= 1 and len(per_row) == 1 and n_img < 128 and (max_len is None or Lt - k + max(per_row) <= max_len):
+                engine = self._ensure_engine()
+                ids = input_ids.to(torch.int64).contiguous()
+                embeds = engine.splice_ids(ids, k, feats_per_image, image_feats)
+                return embeds, [embeds.shape[1]] * B, True
+            out, lens = self._prepare_multimodal(input_ids, None, attention_mask, None, None, images,
+                                                 encoded=(image_feats, feats_per_image))
+            return out[4], lens, False
+        out, lens = self._prepare_multimodal(input_ids, None, attention_mask, None, None, images)
+        return out[4], lens, False
+
+    def _prepare_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images, encoded=None):
         """The reference's 6-tuple plus the per-row valid lengths of the spliced sequence (no state is kept on `self`:
         concurrent calls from several threads must not see each other's lengths)."""
         vision_tower = self.get_vision_tower()
@@ -186,7 +210,7 @@ class LlavaMetaForCausalLM(ABC):
                     position_ids = torch.sum(attention_mask, dim=1).unsqueeze(-1) - 1
             return (input_ids, position_ids, attention_mask, past_key_values, None, labels), None
 
-        image_feats, feats_per_image = self._image_features(images)
+        image_feats, feats_per_image = encoded if encoded is not None else self._image_features(images)
 
         if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
             raise NotImplementedError

@@ -123,10 +123,14 @@ def condition_weights(w, cfg, seed=0, layer_gain=None):
     top-1/top-2 logit margin is of the order of the bf16 noise, so identical ids would be luck. Here the output head is
     tied to a permutation of the embedding table (lm_head[perm[t]] = embed_tokens[t]) and the residual branches
     (o_proj, down_proj) are damped by `layer_gain`, so the final hidden state keeps a cosine of ~0.3-0.5 with the embedding
-    of the token that was fed: the winning logit stands ~|e|^2 cos above a field of ~N(0, |e|^2 / h) competitors — tens of
-    noise widths — while every layer still shapes the state (attention over the whole context and the MLPs contribute
-    the other ~70-95 % of its norm). Greedy ids are then a deterministic, noise-robust function of the model: any two
-    correct implementations must produce the same ids. Returns a NEW dict (tensors not scaled are shared)."""
+    of the token that was fed: the winning logit stands tens of noise widths above the field (measured: margin / bf16 error
+    > 100 on the tiny/small configs, 37 logit-std at 7B depth) while the layers still contribute most of the state's norm.
+    What this buys and what it does not: the winner is then (measured) always perm[last token], so the test cannot see a
+    small numerical error — that is the job of the logit-tolerance tests; it DOES see every plumbing error (token feedback,
+    cache slot / length bookkeeping, batch-row mix-ups, sampling state, path switches), on every decode path, with ids that
+    any correct implementation must reproduce exactly. Loosening the damping until the context decides the token brings
+    the margin back to the noise level (measured: layer_gain 3-4 -> margin/error < 2), which is the original problem.
+    Returns a NEW dict (tensors not scaled are shared)."""
     g = torch.Generator().manual_seed(1000 + seed)
     V = cfg["vocab"]
     if layer_gain is None:

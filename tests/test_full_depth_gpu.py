@@ -4,8 +4,8 @@ the fp32 oracle on the host cores: vision features, last-position prefill logits
 the measured errors written to gpurun_out/full_depth_parity.json; plus STRICT greedy-id equality on the well-conditioned
 weight set (oracle.condition_weights) across the three decode paths (megakernel B=1, GEMV graph B=4, stream-K GEMM B=12).
 
-Stated tolerance at full depth (north_star: "logits within a stated fp tolerance"): max |logit - ref| <= 12 % and mean
-<= 2.5 % of the reference logit std against the fp32 oracle (bf16 rounding of 32-40 residual updates; the same bound the
+Stated tolerance at full depth (north_star: "logits within a stated fp tolerance"): max |logit - ref| <= 10 % and mean
+<= 2 % of the reference logit std against the fp32 oracle (bf16 rounding of 32-40 residual updates; the same bound the
 reference's own bf16 path stays in, see test_model_gpu for the measured bf16-vs-fp32 noise of the restated reference)."""
 import json
 import os
@@ -22,7 +22,7 @@ from llava.model.llava_arch import build_source_index  # noqa: E402
 from oracle import llava_oracle as O  # noqa: E402
 
 DEV, BF = "cuda", torch.bfloat16
-TOL_MAX, TOL_MEAN = 0.12, 0.025
+TOL_MAX, TOL_MEAN = 0.10, 0.02   # measured on B200 (profiles/r2c_full_depth_parity.json): 7B 0.063 / 0.0104, 13B 0.081 / 0.015
 REPORT = {}
 
 
@@ -35,7 +35,9 @@ def _device_weights(cfg, seed):
         if kind == "g":
             t = t + 1.0
         w[key] = t.to(BF)
-    return w, {k: v.cpu() for k, v in w.items()}
+    # the oracle copy is converted to fp32 ONCE (27 GB for 7B, 52 GB for 13B host memory): converting bf16 -> fp32 inside every
+    # oracle matmul made the 41 forward passes of this file cost 5 minutes
+    return w, {k: v.cpu().float() for k, v in w.items()}
 
 
 def _report(name, **kv):
@@ -104,7 +106,7 @@ def test_7b_full_depth_configs1_inputs_vs_fp32_oracle():
     changed = [k for k in wc_cpu if wc_cpu[k] is not w_cpu[k]]
     eng.close()
     for k in changed:
-        w_dev[k] = wc_cpu[k].to(DEV)
+        w_dev[k] = wc_cpu[k].to(DEV, BF)
     eng = make_engine(cfg, w_dev, max_batch=12, max_seq=128, max_images=1)
     g = torch.Generator().manual_seed(5)
     prompt = torch.randint(3, cfg["vocab"], (1, 24), generator=g)

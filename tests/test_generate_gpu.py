@@ -254,7 +254,9 @@ def test_bad_ids_raise_instead_of_reading_out_of_bounds():
     bad = ids.clone()
     bad[0, 3] = cfg["vocab"] + 5
     with pytest.raises(ValueError, match="embedding table"):
-        model.generate(bad.to(DEV), images=images.to(DEV), max_new_tokens=2)       # host check (ids are on the host anyway)
+        model.generate(bad, images=images.to(DEV), max_new_tokens=2)               # host ids: checked while the index is built
+    with pytest.raises(ValueError, match="token id"):
+        model.generate(bad.to(DEV), images=images.to(DEV), max_new_tokens=2)       # device ids: flagged by the gather kernel
     with pytest.raises(ValueError, match="token id"):
         model.generate(bad.to(DEV), images=None, max_new_tokens=2)                 # text path: flagged by the kernel
     with pytest.raises(ValueError, match="token id"):
@@ -265,3 +267,109 @@ def test_bad_ids_raise_instead_of_reading_out_of_bounds():
         model.generate(ids.to(DEV), images=images.to(DEV), max_new_tokens=2, repetition_penalty=1.2)
     model.generate(ids.to(DEV), images=images.to(DEV), max_new_tokens=2, repetition_penalty=1.0)  # the "off" value is fine
     model.invalidate_engine()
+
+
+# ------------------------------------------------------------------------------------------------ device-side splice
+def test_device_splice_equals_host_index(tiny_engine):
+    """b2_splice_ids (index built by a kernel from ids that stay on the device) == b2_splice over the host-built index, which
+    tests/test_splice_host.py pins against the unmodified reference; a wrong placeholder count is flagged, never misread."""
+    from llava.model.llava_arch import build_source_index
+
+    cfg, _, eng = tiny_engine
+    P, h = 16, cfg["hidden"]
+    g = torch.Generator().manual_seed(11)
+    for B, Lt, k, group in [(1, 12, 1, 1), (1, 40, 2, 1), (3, 9, 1, 1), (2, 17, 3, 1), (2, 11, 1, 2), (4, 130, 2, 1), (1, 700, 1, 1)]:
+        n_img = B * k
+        feat_rows = [P * group] * n_img
+        feats = torch.randn(sum(feat_rows), h, generator=g).to(torch.bfloat16).to(DEV)
+        ids = torch.randint(3, cfg["vocab"], (B, Lt), generator=g)
+        for b in range(B):
+            pos = torch.randperm(Lt - 1, generator=g)[:k] + 1
+            ids[b, pos] = O.IMAGE_TOKEN_INDEX
+        assert (Lt - k + k * P * group) * B <= 16 * 160  # this fixture's workspace
+        got = eng.splice_ids(ids.to(DEV), k, feat_rows, feats)
+        src, _, _, _, lens = build_source_index(ids.numpy(), np.ones((B, Lt), bool), np.full((B, Lt), -100), feats.shape[0],
+                                                feat_rows, None, "right")
+        want = eng.splice(torch.from_numpy(src.reshape(-1)).to(DEV), feats, B, src.shape[1])
+        torch.cuda.synchronize()
+        assert eng.take_async_error() == 0
+        assert got.shape == want.shape and torch.equal(got, want), (B, Lt, k, group)
+    # one placeholder too few / too many: flagged
+    ids = torch.randint(3, cfg["vocab"], (1, 20), generator=g)
+    ids[0, 4] = O.IMAGE_TOKEN_INDEX
+    feats = torch.randn(2 * P, h, generator=g).to(torch.bfloat16).to(DEV)
+    eng.splice_ids(ids.to(DEV), 2, [P, P], feats)
+    torch.cuda.synchronize()
+    assert eng.take_async_error() & _b2.ERR_SPLICE_SLOTS
+    ids[0, 9] = ids[0, 12] = O.IMAGE_TOKEN_INDEX
+    eng.splice_ids(ids.to(DEV), 2, [P, P], feats)
+    torch.cuda.synchronize()
+    assert eng.take_async_error() & _b2.ERR_SPLICE_SLOTS
+
+
+def test_generate_with_device_ids_falls_back_to_reference_semantics_on_odd_inputs():
+    """two images but ONE placeholder: the reference uses the first image and ignores the second (llava_arch.py:149-181).
+    The device path assumes n_images / B placeholders per row, notices on its first sync that the assumption failed, and
+    redoes the splice on the host path: same result as host-resident ids."""
+    cfg, model = _tiny_model()
+    ids, images = synth_inputs(cfg, B=1, Lt=12, seed=3)
+    two = torch.cat([images, images.flip(-1)])
+    a = model.generate(ids, images=two.to(DEV), do_sample=False, max_new_tokens=8, eos_token_id=[])          # host path
+    b = model.generate(ids.to(DEV), images=two.to(DEV), do_sample=False, max_new_tokens=8, eos_token_id=[])  # device -> fallback
+    c = model.generate(ids.to(DEV), images=images.to(DEV), do_sample=False, max_new_tokens=8, eos_token_id=[])  # device path
+    assert torch.equal(a.cpu(), b.cpu()) and torch.equal(a.cpu(), c.cpu())
+    model.invalidate_engine()
+
+
+# ------------------------------------------------------------------------------------------------ continuous batching
+def test_continuous_batching_of_concurrent_generate_threads():
+    """six worker threads call generate() on ONE model (the reference worker's pattern, model_worker.py:174-185,
+    230-243); with config.b2_continuous_batching = 4 their decode steps are shared. On the well-conditioned weight set every
+    request must produce exactly the ids it produces alone on an unbatched model — requests join and leave the batch at
+    different steps (different prompt lengths, max_new_tokens, one keyword stop, one sampled request)."""
+    cfg = O.CONFIGS["tiny"]
+    wc = O.condition_weights(O.make_weights(cfg, seed=0), cfg, seed=0)
+    solo = make_model(cfg, wc, max_batch=1, max_seq=160)
+    batched = make_model(cfg, wc, max_batch=4, max_seq=160, b2_continuous_batching=4)
+    jobs = []
+    for i in range(6):
+        ids, images = synth_inputs(cfg, B=1, Lt=9 + 4 * i, seed=40 + i)
+        jobs.append(dict(ids=ids.to(DEV), images=images.to(DEV), n=10 + 7 * i))
+    tok = CharTokenizer()
+
+    def run(model, j, i):
+        kw = dict(do_sample=False, max_new_tokens=j["n"], eos_token_id=[])
+        if i == 2:  # a keyword stop that fires mid-way (computed from the solo run below)
+            kw["stopping_criteria"] = [KeywordStop(j["keyword"], tok, j["ids"])]
+        if i == 4:
+            torch.manual_seed(123)
+            kw.update(do_sample=True, temperature=0.8, top_p=0.9)
+        return model.generate(j["ids"], images=j["images"], **kw).cpu()
+
+    free = solo.generate(jobs[2]["ids"], images=jobs[2]["images"], do_sample=False, max_new_tokens=jobs[2]["n"], eos_token_id=[])
+    jobs[2]["keyword"] = tok.decode(free[0, jobs[2]["ids"].shape[1]:].cpu())[5:8]
+    want = [run(solo, j, i) for i, j in enumerate(jobs)]
+    got, errors = [None] * 6, []
+
+    def work(i):
+        try:
+            got[i] = run(batched, jobs[i], i)
+        except Exception as e:  # pragma: no cover
+            errors.append((i, e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(6):
+        if i == 4:  # sampled: same prompt echo and length; the draw stream differs from the solo run by construction (row index)
+            assert got[i].shape == want[i].shape
+            continue
+        assert torch.equal(got[i], want[i]), (i, got[i], want[i])
+    st = batched._batcher.stats
+    assert st["admitted"] == 6 and st["max_active"] >= 2 and st["rows_stepped"] > st["steps"], st   # steps really were shared
+    # a second wave reuses the freed slots (ring tags / slot resets)
+    again = run(batched, jobs[1], 1)
+    assert torch.equal(again, want[1])
+    batched.invalidate_engine()
+    solo.invalidate_engine()

@@ -391,3 +391,29 @@ def test_error_convention():
     with pytest.raises(ValueError):
         eng.decode_step(kv, torch.zeros(1, dtype=torch.int32))  # empty cache
     eng.close()
+
+
+@pytest.mark.parametrize("n_img", [1, 3, 20])
+def test_fused_projector_kernel_equals_the_two_gemm_form(n_img):
+    """north_star: "mm_projector as one fused GEMM->GELU->GEMM kernel". The single-launch kernel (phase-2 tiles gated on
+    per-row-block completion counters) against the two-launch form of the same GEMM (B2_PROJECTOR_FUSED=0) and the oracle,
+    at the 7B projector shape; 20 images = 90 row blocks = 12 dependency groups, repeated to catch a stale read of H."""
+    cfg = O.make_config(hidden=4096, inter=11008, layers=1, heads=32, vit_layers=2)
+    w = O.make_weights(cfg, seed=21)
+    eng = make_engine(cfg, w, max_batch=1, max_seq=32, max_images=n_img)
+    g = torch.Generator().manual_seed(n_img)
+    feats = (torch.randn(n_img, 576, 1024, generator=g)).to(torch.bfloat16)
+    ref = O.mm_projector(w, feats.float())
+    try:
+        os.environ["B2_PROJECTOR_FUSED"] = "0"
+        two = eng.project(feats.to(DEV)).float().cpu()
+        os.environ["B2_PROJECTOR_FUSED"] = "1"
+        for rep in range(4):
+            one = eng.project(feats.to(DEV)).float().cpu()
+            assert torch.isfinite(one).all()
+            # same operands, same fp32 accumulation order per output element (tile width may differ): <= 1 bf16 ulp apart
+            torch.testing.assert_close(one, two, rtol=2 ** -7, atol=1e-3)
+    finally:
+        os.environ.pop("B2_PROJECTOR_FUSED", None)
+    _check(f"fused projector ({n_img} images)", one, ref)
+    eng.close()
