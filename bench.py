@@ -439,6 +439,26 @@ def extra_configs(args, dev, model7b):
                 "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                              "frac": flops / (ms * 1e-3) / 1e12 / tf_peak, "peak_source": peak_kind}})
     del px
+    # the same 256 images starting from uint8 HWC frames on the HOST: H2D + PIL-exact resize / pad / normalise kernels
+    # (llava/_b2/preprocess.py, replaces mm_utils.process_images) + encode_images, wall clock
+    try:
+        import numpy as np
+        from llava._b2.preprocess import ClipPreprocessor
+        pre = ClipPreprocessor(model7b.get_vision_tower().image_processor, device=dev, image_aspect_ratio="pad")
+        rng = np.random.default_rng(0)
+        frames = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(32)] * 8
+        eng.encode_images(pre(frames))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            eng.encode_images(pre(frames))
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 2
+        out[-1]["from_uint8_host_frames"] = {"value": 256 / dt, "unit": "images/s", "ms_per_step": dt * 1e3,
+                                             "input": "256 x uint8 [480,640,3] on the host, image_aspect_ratio=pad",
+                                             "h2d_bytes_per_step": 256 * 480 * 640 * 3}
+    except Exception as e:
+        out[-1]["from_uint8_host_frames"] = {"error": repr(e)[:300]}
     # the "bs=32" half of the metric, 7B
     r = measure_device_resident(eng, m7, 32, S, N, steps, warm, dev=dev, isolate_decode=True, sampler=ClockSampler(dev.index or 0))
     out.append(config_line("LLaVA-1.5-7B bf16 bs=32: 576+%d prefill, %d-token decode" % (args.prompt, N), m7, 32, S, N, r))
@@ -528,20 +548,21 @@ def measure_e2e_stream(model, ids_host, images_host, N, steps, warmup):
 
 
 def ncu_traffic_from_profile():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch from the newest committed `ncu --set full`
-    summary under profiles/ (parsed at run time; null when no capture is committed)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch, parsed at run time from the newest committed
+    `ncu --set full` summary under profiles/ (lines `metric  value  unit`); null when no capture is committed."""
     import glob
     import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_mega_ncu_full.txt"))):
         txt = open(path).read()
-        rd = re.search(r"dram__bytes_read\.sum\s+\S*\s+([\d.,e+]+)", txt)
-        wr = re.search(r"dram__bytes_write\.sum\s+\S*\s+([\d.,e+]+)", txt)
-        if rd and wr:
-            try:
-                best = (float(rd.group(1).replace(",", "")) + float(wr.group(1).replace(",", "")), os.path.basename(path))
-            except ValueError:
-                pass
+        vals = []
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            mt = re.search(r"^" + re.escape(name) + r"\s+([\d.,]+)\s+(\w+)\s*$", txt, re.M)
+            if mt and mt.group(2) in unit:
+                vals.append(float(mt.group(1).replace(",", "")) * unit[mt.group(2)])
+        if len(vals) == 2:
+            best = (vals[0] + vals[1], os.path.basename(path))
     return best
 
 

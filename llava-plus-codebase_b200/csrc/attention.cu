@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(DecodeAttnParam
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = (warp << 1) | (lane >> 4);  // half-warp id 0..7
     const int c = lane & 15;                   // 8-element chunk of the head dim
+    pdl_trigger();
+    pdl_wait();                                // qkv (previous GEMM) and cur_len (previous step) are upstream outputs
     const int pos = p.cur_len[b];              // position of the new token == number of cached keys
     const int total = pos + 1;
     const int hd = p.H * DA_D;
@@ -559,7 +561,7 @@ int decode_attn_bf16(const DecodeAttnArgs& a, cudaStream_t stream) {
     p.theta = a.theta;
     p.scale_log2 = a.scale * 1.4426950408889634f;
     dim3 grid(a.nsplit, a.H, a.B);
-    decode_attn_kernel<<<grid, DA_THREADS, 0, stream>>>(p);
+    B2_CUDA_CHECK(launch_pdl(decode_attn_kernel, grid, dim3(DA_THREADS), 0, stream, p));
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -50,6 +50,27 @@ extern unsigned long long g_launch_count;  // kernels launched by this library (
     } while (0)
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in the stream
+// is still draining; everything it does BEFORE pdl_wait() must not touch memory the predecessor writes or reads-then-expects
+// unchanged. Kernels of the decode step use the window to fetch WEIGHTS (which no kernel writes) into shared memory.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // B2_PDL=0 turns the launch attribute off (A/B runs)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

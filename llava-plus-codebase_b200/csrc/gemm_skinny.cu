@@ -123,17 +123,38 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    pdl_trigger();  // the next kernel of the step may start its own weight prefetch as soon as it finds room on an SM
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer: weights are read exactly once -> evict-first; activations stay in L2 =====
+            // Programmatic dependent launch: this CTA may be running while the kernel that PRODUCES x is still finishing.
+            // Weights depend on nothing, so the first ring-full of W tiles is requested right away; the activation half of
+            // those stages follows once the upstream grid has completed (pdl_wait), everything after that runs as usual.
             int stage = 0; uint32_t phase = 0;
+            int pre_n = 0;                      // stages whose W half is already in flight
+            {
+                int t = t_first;
+                int kb = (int)(u0 - (long long)t * nkb);
+                long long u = u0;
+                while (u < u1 && pre_n < STAGES) {
+                    uint8_t* sw = smem + pre_n * Cfg::STAGE;
+                    mbar_arrive_expect_tx(&full_bar[pre_n], Cfg::STAGE);
+                    tma_load_2d(sw, &tmap_w, &full_bar[pre_n], kb * BKE, t * SK_BM, kEvictFirst);
+                    ++pre_n; ++u;
+                    if (++kb == nkb) { kb = 0; ++t; }
+                }
+            }
+            pdl_wait();
+            int seen = 0;
             for (int t = t_first; t <= t_last; ++t) {
                 const int kb0 = (int)(max(u0, (long long)t * nkb) - (long long)t * nkb);
                 const int kb1 = (int)(min(u1, (long long)(t + 1) * nkb) - (long long)t * nkb);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                for (int kb = kb0; kb < kb1; ++kb, ++seen) {
                     uint8_t* sw = smem + stage * Cfg::STAGE;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
-                    tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * BKE, t * SK_BM, kEvictFirst);
+                    if (seen >= pre_n) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
+                        tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * BKE, t * SK_BM, kEvictFirst);
+                    }
                     tma_load_2d(sw + SK_W_TILE, &tmap_x, &full_bar[stage], kb * BKE, 0, kEvictLast);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -169,6 +190,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         }
     } else {
         // ===== epilogue warps 2..5 =====
+        pdl_wait();                           // residual / out / the stream-K workspace are shared with upstream kernels
         const int q = warp & 3;               // TMEM lane quadrant
         const int row_in_tile = q * 32 + lane;
         const int et = threadIdx.x - 64;      // 0..127
@@ -306,7 +328,7 @@ int sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkPlan& pl, in
         B2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set = true;
     }
-    kern<<<pl.grid, SK_THREADS, Cfg::SMEM, st>>>(tw, tx, N, K, B, ep);
+    B2_CUDA_CHECK(launch_pdl(kern, dim3(pl.grid), dim3(SK_THREADS), (size_t)Cfg::SMEM, st, tw, tx, N, K, B, ep));
     B2_LAUNCH_CHECK();
     return 0;
 }

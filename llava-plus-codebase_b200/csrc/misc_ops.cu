@@ -48,6 +48,8 @@ __global__ void splice_embed_kernel(const int32_t* __restrict__ src_index, const
 __global__ void embed_tokens_kernel(const int32_t* __restrict__ tokens, const uint4* __restrict__ table,
                                     uint4* __restrict__ out, int vec_per_row, int vocab, int* err_flag) {
     const int row = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();  // tokens come from the previous step's selection kernel
     int32_t t = tokens[row];
     if ((t < 0 || t >= vocab) && threadIdx.x == 0 && err_flag) report_err(err_flag, B2_ERR_TOKEN_RANGE);
     t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);  // never read out of bounds
@@ -226,8 +228,8 @@ int splice_embed(const int32_t* src_index, const void* table, const void* feats,
 int embed_tokens(const int32_t* tokens, const void* table, void* out, int rows, int h, int vocab, int* err_flag,
                  cudaStream_t stream) {
     B2_CHECK_ARG(h % 8 == 0 && rows > 0, "embed_tokens: bad shape rows=%d h=%d", rows, h);
-    embed_tokens_kernel<<<rows, 128, 0, stream>>>(tokens, reinterpret_cast<const uint4*>(table),
-                                                  reinterpret_cast<uint4*>(out), h / 8, vocab, err_flag);
+    B2_CUDA_CHECK(launch_pdl(embed_tokens_kernel, dim3(rows), dim3(128), 0, stream, tokens, reinterpret_cast<const uint4*>(table),
+                             reinterpret_cast<uint4*>(out), h / 8, vocab, err_flag));
     B2_LAUNCH_CHECK();
     return 0;
 }

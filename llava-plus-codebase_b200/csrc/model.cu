@@ -22,6 +22,11 @@ namespace b2 {
 static thread_local char g_err[1024] = {0};
 unsigned long long g_launch_count = 0;
 
+bool pdl_enabled() {  // read per launch (one getenv) so that one process can A/B it; graphs keep what they were captured with
+    const char* e = getenv("B2_PDL");
+    return !(e != nullptr && e[0] == '0');
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -112,6 +112,8 @@ rmsnorm_row_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_row_stride, co
                    const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ y, int cols, float eps) {
     __shared__ float s_part[8];
     const int row = blockIdx.x, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();  // x is the previous kernel's output
     const int64_t src_row = row_index != nullptr ? (int64_t)row_index[row] : (int64_t)row;
     const __nv_bfloat16* xr = x + src_row * x_row_stride;
     const int nvec = cols >> 3;
@@ -174,9 +176,9 @@ static int rmsnorm_launch(const void* x, int64_t stride, const int32_t* row_inde
     B2_CHECK_ARG(rows > 0 && cols > 0 && cols % 256 == 0,
                  "rmsnorm: cols must be a multiple of 256 (cols=%d rows=%d)", cols, rows);
     if (rows < 4096 && cols <= 8192) {  // few rows: a CTA per row keeps every SM busy and the row in registers
-        rmsnorm_row_kernel<<<rows, 256, 0, stream>>>(
-            reinterpret_cast<const __nv_bfloat16*>(x), stride, row_index,
-            reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<__nv_bfloat16*>(y), cols, eps);
+        B2_CUDA_CHECK(launch_pdl(rmsnorm_row_kernel, dim3(rows), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
+                                 stride, row_index, reinterpret_cast<const __nv_bfloat16*>(gamma),
+                                 reinterpret_cast<__nv_bfloat16*>(y), cols, eps));
         B2_LAUNCH_CHECK();
         return 0;
     }

@@ -154,6 +154,8 @@ sample_publish_kernel(const float* __restrict__ logits, int V, int B, SampleStat
     __shared__ int s_choice;
 
     const int tid = threadIdx.x, b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();  // logits / tok / the selection state are outputs of earlier kernels in the stream
     const bool per_row = st->per_row != 0;
     const bool active = !per_row || rows[b].active != 0;
     const int do_sample = per_row ? rows[b].do_sample : st->do_sample;
@@ -307,8 +309,8 @@ int sample_publish(const float* logits, int V, int B, SampleState* st_dev, RowSt
         B2_CUDA_CHECK(cudaFuncSetAttribute(sample_publish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    sample_publish_kernel<<<B, SP_THREADS, smem, stream>>>(logits, V, B, st_dev, rows_dev, tok, out_tokens, step_counter, cur_len,
-                                                           ring_dev, ring_cap, flags, step_offset);
+    B2_CUDA_CHECK(launch_pdl(sample_publish_kernel, dim3(B), dim3(SP_THREADS), smem, stream, logits, V, B, st_dev, rows_dev, tok,
+                             out_tokens, step_counter, cur_len, ring_dev, ring_cap, flags, step_offset));
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -65,7 +65,7 @@ def main():
                     kv.reset()
                     first = engine.argmax(engine.prefill(kv, embeds, lens, _b2.LOGITS_LAST))
                     torch.cuda.synchronize()
-                    time.sleep(0.2)
+                    time.sleep(float(env.get("SLEEP", "0.2")))
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     t0 = time.perf_counter()
@@ -74,12 +74,29 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     times.append(e0.elapsed_time(e1) / N)
+                # time evolution inside one run: 8-step chunks back to back (is a run slower at its end than at its start?)
+                kv.reset()
+                first = engine.argmax(engine.prefill(kv, embeds, lens, _b2.LOGITS_LAST))
+                torch.cuda.synchronize()
+                sampler = bench.ClockSampler(0)
+                sampler.start()
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(N // 8 + 1)]
+                cur = first
+                evs[0].record()
+                for c in range(N // 8):
+                    chunk = engine.decode_greedy(kv, cur, 8)
+                    cur = chunk[7]
+                    evs[c + 1].record()
+                torch.cuda.synchronize()
+                clocks = sampler.stop()
+                chunks = [round(evs[c].elapsed_time(evs[c + 1]) / 8, 3) for c in range(N // 8)]
                 toks = out.cpu()
                 if ref is None:
                     ref = toks.clone()
                 best = min(times[1:])
                 gbs = work["decode_bytes_per_step"] / best / 1e6
                 d = dict(B=B, variant=variant, ms_per_step=best, all_ms=times, host_enqueue_ms_per_step=min(host[1:]),
+                         ms_per_step_by_8_step_chunk=chunks, clocks=clocks,
                          frac_hbm_peak=gbs / hbm_peak, tokens_equal_first_variant=bool((toks == ref).all()))
                 s = json.dumps(d)
                 print(s, flush=True)
