@@ -264,6 +264,8 @@ __global__ void __launch_bounds__(256)
 rope_kv_write_kernel(__nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
                      __nv_bfloat16* __restrict__ vcache, int S, int H, int D, int Smax, float theta) {
     __shared__ float s_c[128], s_s[128];  // D/2 <= 128
+    pdl_trigger();
+    pdl_wait();  // inputs are outputs of the upstream kernel (programmatic dependent launch)
     const int row = blockIdx.x;  // b*S + t
     const int b = row / S, t = row % S;
     const int hd = H * D;
@@ -539,9 +541,8 @@ int rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, in
     B2_CHECK_ARG(D % 16 == 0 && D <= 256, "rope_kv_write: head_dim must be a multiple of 16, <= 256 (got %d)", D);
     B2_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(kcache) |
                    reinterpret_cast<uintptr_t>(vcache)) & 15) == 0, "rope_kv_write: buffers must be 16-byte aligned");
-    rope_kv_write_kernel<<<B * S, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(qkv),
-                                                    reinterpret_cast<__nv_bfloat16*>(kcache),
-                                                    reinterpret_cast<__nv_bfloat16*>(vcache), S, H, D, Smax, theta);
+    B2_CUDA_CHECK(launch_pdl(rope_kv_write_kernel, dim3(B * S), dim3(256), 0, stream, reinterpret_cast<__nv_bfloat16*>(qkv),
+                             reinterpret_cast<__nv_bfloat16*>(kcache), reinterpret_cast<__nv_bfloat16*>(vcache), S, H, D, Smax, theta));
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -120,6 +120,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * TC_BM;
     const int head = blockIdx.y, b = blockIdx.z;
+    pdl_trigger();
+    pdl_wait();  // q/k/v (and seq_lens) are outputs of upstream kernels (programmatic dependent launch)
     const int len = p.seq_lens != nullptr ? p.seq_lens[b] : p.S;
     const int kv_end = CAUSAL ? min(len, q0 + TC_BM) : len;
     const int n_tiles = (kv_end + TC_BN - 1) / TC_BN;  // >= 1 (len >= 1)
@@ -379,7 +381,7 @@ int launch_tc(const FlashArgs& a, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid((a.S + TC_BM - 1) / TC_BM, a.H, a.B);
-    kern<<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, p);
+    B2_CUDA_CHECK(launch_pdl(kern, grid, dim3(TC_THREADS), (size_t)smem, stream, tq, tk, tv, p));
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -158,6 +158,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     cluster_sync_all();  // barriers initialised and TMEM allocated in both CTAs before anyone signals across
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();  // set-up above overlapped the upstream kernel's tail (programmatic dependent launch); A / residual are its outputs
 
     if (warp == 0) {
         if (lane == 0) {
@@ -317,7 +319,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int 
     const int tiles = ((M + P_TM - 1) / P_TM) * ((N + P_TN - 1) / P_TN);
     const int max_pairs = num_sms() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    kern<<<2 * pairs, P_THREADS, P_SMEM, stream>>>(ta, tb, M, N, K, ep);  // cluster dims (2,1,1) are a kernel attribute
+    B2_CUDA_CHECK(launch_pdl(kern, dim3(2 * pairs), dim3(P_THREADS), (size_t)P_SMEM, stream, ta, tb, M, N, K, ep));  // cluster dims (2,1,1) are a kernel attribute
     B2_LAUNCH_CHECK();
     return 0;
 }

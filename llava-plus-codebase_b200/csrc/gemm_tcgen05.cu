@@ -192,21 +192,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    pdl_trigger();
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
         if (lane == 0) {
+            // Programmatic dependent launch: the WEIGHT halves of the first ring-full of stages are requested before the
+            // upstream kernel (which produces A) is known to have finished; the A halves follow after pdl_wait().
             int stage = 0;
             uint32_t phase = 0;
+            int pre_n = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                int m_blk, n_blk;
+                tile_coords(blockIdx.x, m_blk, n_blk);
+                for (int kb = 0; kb < num_kb && pre_n < STAGES; ++kb, ++pre_n) {
+                    uint8_t* sb = smem + pre_n * Cfg::STAGE_BYTES + A_TILE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[pre_n], Cfg::STAGE_BYTES);
+                    tma_load_2d(sb, &tmap_b, &full_bar[pre_n], kb * BK, n_blk * BN, kEvictNormal);
+                }
+            }
+            pdl_wait();
+            int seen = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                for (int kb = 0; kb < num_kb; ++kb, ++seen) {
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_TILE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (seen >= pre_n) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN, kEvictNormal);
+                    }
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM, kEvictNormal);
-                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN, kEvictNormal);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -243,6 +260,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else {
         // ===================== epilogue warps 2..9 =====================
+        pdl_wait();                        // residual / out may be read or written by the upstream kernel
         const int q = warp & 3;            // TMEM lane quadrant this warp may access (warp_id % 4)
         const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the tile's columns
         int local = 0;
@@ -441,6 +459,7 @@ projector_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
+            pdl_wait();   // X comes from the vision tower's last kernel
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const FpTile tl = fp_tile(t, num_m, nn1, nn2);
@@ -494,6 +513,7 @@ projector_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         }
     } else {
         // ===== epilogue warps 2..9: bias (+ erf-GELU in phase 1), bf16 stores; phase 1 publishes the row block =====
+        pdl_wait();
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         int local = 0;
@@ -566,7 +586,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int 
     }
     const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+    B2_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), (size_t)Cfg::SMEM_BYTES, stream, ta, tb, M, N, K, ep));
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -597,7 +617,7 @@ int launch_fused_projector(const CUtensorMap& tx, const CUtensorMap& tw1, const 
     const int num_m = (P.M + BM - 1) / BM;
     const int tiles = num_m * ((P.N1 + BN - 1) / BN + (P.N2 + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();  // <= #SMs, 1 CTA/SM: every CTA is resident (the spin needs it)
-    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(tx, tw1, th, tw2, P);
+    B2_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), (size_t)Cfg::SMEM_BYTES, stream, tx, tw1, th, tw2, P));
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, int cols,
                  float eps) {
+    pdl_trigger();
+    pdl_wait();  // inputs are outputs of the upstream kernel (programmatic dependent launch)
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_row_stride, const int32_t* __restrict__ row_index,
                const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ y, int rows, int cols,
                float eps) {
+    pdl_trigger();
+    pdl_wait();  // inputs are outputs of the upstream kernel (programmatic dependent launch)
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -164,9 +168,9 @@ int layernorm_bf16(const void* x, const void* gamma, const void* beta, void* y, 
     B2_CHECK_ARG(rows > 0 && cols > 0 && cols % 256 == 0 && cols <= 2048,
                  "layernorm: cols must be a multiple of 256 and <= 2048 (cols=%d rows=%d)", cols, rows);
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    layernorm_kernel<8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+    B2_CUDA_CHECK(launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma),
-        reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps);
+        reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps));
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -183,9 +187,9 @@ static int rmsnorm_launch(const void* x, int64_t stride, const int32_t* row_inde
         return 0;
     }
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    rmsnorm_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+    B2_CUDA_CHECK(launch_pdl(rmsnorm_kernel, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream,
         reinterpret_cast<const __nv_bfloat16*>(x), stride, row_index,
-        reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps);
+        reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps));
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -12,6 +12,8 @@ namespace {
 // one CTA per patch; threads sweep the kpad output elements (k = c*ps*ps + i*ps + j)
 __global__ void vit_im2col_kernel(const __nv_bfloat16* __restrict__ pix, __nv_bfloat16* __restrict__ out, int img,
                                   int ps, int kpad) {
+    pdl_trigger();
+    pdl_wait();  // inputs are outputs of the upstream kernel (programmatic dependent launch)
     const int grid_w = img / ps;
     const int P = grid_w * grid_w;
     const int bp = blockIdx.x;
@@ -37,6 +39,8 @@ vit_embed_ln_kernel(const __nv_bfloat16* __restrict__ patch_out, const __nv_bflo
                     const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ gamma,
                     const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ hidden, int B, int P,
                     int D, float eps) {
+    pdl_trigger();
+    pdl_wait();  // inputs are outputs of the upstream kernel (programmatic dependent launch)
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int T = P + 1;
@@ -97,6 +101,8 @@ vit_embed_ln_kernel(const __nv_bfloat16* __restrict__ patch_out, const __nv_bflo
 
 __global__ void vit_drop_cls_kernel(const uint4* __restrict__ hidden, uint4* __restrict__ out, int P, int vec_per_row,
                                     int64_t total_vec) {
+    pdl_trigger();
+    pdl_wait();  // inputs are outputs of the upstream kernel (programmatic dependent launch)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_vec) return;
     const int64_t row = i / vec_per_row;  // b*P + p
@@ -111,8 +117,8 @@ int vit_im2col(const void* pixels, void* out, int B, int img, int patch, int kpa
     B2_CHECK_ARG(img % patch == 0 && kpad >= 3 * patch * patch && kpad % 8 == 0,
                  "vit_im2col: bad geometry img=%d patch=%d kpad=%d", img, patch, kpad);
     const int P = (img / patch) * (img / patch);
-    vit_im2col_kernel<<<B * P, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pixels),
-                                                 reinterpret_cast<__nv_bfloat16*>(out), img, patch, kpad);
+    B2_CUDA_CHECK(launch_pdl(vit_im2col_kernel, dim3(B * P), dim3(128), 0, stream, reinterpret_cast<const __nv_bfloat16*>(pixels),
+                             reinterpret_cast<__nv_bfloat16*>(out), img, patch, kpad));
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -121,10 +127,10 @@ int vit_embed_ln(const void* patch_out, const void* cls, const void* pos, const 
                  void* hidden, int B, int P, int D, float eps, cudaStream_t stream) {
     B2_CHECK_ARG(D % 256 == 0 && D <= 2048, "vit_embed_ln: D must be a multiple of 256 and <= 2048 (D=%d)", D);
     const int rows = B * (P + 1);
-    vit_embed_ln_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(
+    B2_CUDA_CHECK(launch_pdl(vit_embed_ln_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream,
         reinterpret_cast<const __nv_bfloat16*>(patch_out), reinterpret_cast<const __nv_bfloat16*>(cls),
         reinterpret_cast<const __nv_bfloat16*>(pos), reinterpret_cast<const __nv_bfloat16*>(gamma),
-        reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(hidden), B, P, D, eps);
+        reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(hidden), B, P, D, eps));
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -134,8 +140,8 @@ int vit_drop_cls(const void* hidden, void* out, int B, int P, int D, cudaStream_
     const int vec_per_row = D / 8;
     const int64_t total = (int64_t)B * P * vec_per_row;
     const int grid = (int)((total + 255) / 256);
-    vit_drop_cls_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(hidden),
-                                                  reinterpret_cast<uint4*>(out), P, vec_per_row, total);
+    B2_CUDA_CHECK(launch_pdl(vit_drop_cls_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(hidden),
+                             reinterpret_cast<uint4*>(out), P, vec_per_row, total));
     B2_LAUNCH_CHECK();
     return 0;
 }

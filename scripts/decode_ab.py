@@ -61,7 +61,10 @@ def main():
                     os.environ[k] = v
                 kv = engine.new_kv(B, S + N + 8)  # fresh cache -> freshly captured graph under this environment
                 times, host = [], []
-                for _ in range(4):
+                for rep in range(int(env.get("REPS", "4"))):
+                    if env.get("FRESHKV") == "1" and rep > 0:   # is a run only fast on a cache object that was just created?
+                        kv.close()
+                        kv = engine.new_kv(B, S + N + 8)
                     kv.reset()
                     first = engine.argmax(engine.prefill(kv, embeds, lens, _b2.LOGITS_LAST))
                     torch.cuda.synchronize()

@@ -23,6 +23,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def launches(tag, name="launches.csv"):
+    name = name if os.path.exists(os.path.join(OUT, name)) else f"{tag}_launches.csv"
     path = os.path.join(OUT, name)
     if not os.path.exists(path):
         return
@@ -75,8 +76,9 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
-    for rep in ("prof_gemv", "prof_gemm", "prof_mega"):
-        full(tag, rep)
+    import glob
+    for path in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):
+        full(tag, os.path.basename(path)[:-len(".ncu-rep")])
     for f in ("bench_n1.json",):
         if os.path.exists(os.path.join(OUT, f)):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, f"{tag}_{f}"))
