@@ -146,6 +146,7 @@ struct MegaParams {
     int l2_ahead = 0;       // weight tiles pulled into L2 in front of the shared-memory ring (0 = off), multiple of 4
     int l2_mode = 1;        // 1 = prefetch.global.L2 lines (LSU), 2 = cp.async.bulk.prefetch.L2 (TMA queue)
     int fast_prologue = 0;  // single-pass activation staging with pre-barrier RMSNorm-weight loads
+    int gamma_smem = 0;     // next phase's RMSNorm weights staged in shared memory (cp.async) in front of the grid barrier
     long long* trace = nullptr;  // optional [n_phases+2][4] SM-clock timestamps of CTA 0 (B2_MEGA_TRACE=1)
     // token publication to the host ring (sampling.cu): non-null only for greedy streaming; with do_sample the separate
     // sample_publish kernel that follows the launch overrides the fused argmax and publishes instead

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from llava import _b2  # noqa: E402
 
 SHAPES = [  # B, S, H, D, causal
-    (1, 577, 16, 64, 0), (8, 577, 16, 64, 0), (32, 577, 16, 64, 0),
+    (1, 577, 16, 64, 0), (8, 577, 16, 64, 0), (32, 577, 16, 64, 0), (64, 577, 16, 64, 0),
     (1, 704, 32, 128, 1), (8, 704, 32, 128, 1), (32, 704, 32, 128, 1),
     (4, 2048, 32, 128, 1), (4, 2048, 40, 128, 1),
 ]
@@ -22,11 +22,12 @@ def main():
     lib = _b2.load_library()
     _b2.check(lib.b2_init(0))
     dev = torch.device("cuda:0")
-    variants = [("tcgen05 2cta/SM@d64", "1", "2"), ("tcgen05 1cta/SM", "1", "1"), ("mma.sync", "0", "1")]
-    for (tag, tc, ctas), (B, S, H, D, causal) in [(v, sh) for sh in SHAPES for v in variants]:
+    variants = [("tcgen05 2cta/SM@d64, exp2 half on FMA pipe", "1", "2", "1"), ("tcgen05 2cta/SM@d64, exp2 all MUFU", "1", "2", "0"),
+                ("tcgen05 1cta/SM", "1", "1", "1"), ("mma.sync", "0", "1", "1")]
+    for (tag, tc, ctas, poly), (B, S, H, D, causal) in [(v, sh) for sh in SHAPES for v in variants]:
         if ctas == "1" and tc == "1" and D != 64:
             continue  # d=128 has a single tcgen05 build
-        os.environ["B2_FLASH_TC"], os.environ["B2_FLASH_TC_CTAS"] = tc, ctas
+        os.environ["B2_FLASH_TC"], os.environ["B2_FLASH_TC_CTAS"], os.environ["B2_FLASH_EXP_POLY"] = tc, ctas, poly
         g = torch.Generator(device=dev).manual_seed(1)
         q, k, v = (torch.randn(B, S, H, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
         o = torch.empty_like(q)

@@ -58,10 +58,12 @@ def main():
         kv = engine.new_kv(B, S + N + 8)
         out_tokens = torch.empty(N, B, dtype=torch.int32, device=dev)
         for cfg in a.configs.split(";"):
-            ahead, mode, fast = (int(x) for x in cfg.split(","))
+            fields = [int(x) for x in cfg.split(",")] + [0]
+            ahead, mode, fast, gsm = fields[:4]
             os.environ["B2_MEGA_L2_AHEAD"] = str(ahead)
             os.environ["B2_MEGA_L2_MODE"] = str(mode)
             os.environ["B2_MEGA_FAST_PROLOGUE"] = str(fast)
+            os.environ["B2_MEGA_GAMMA_SMEM"] = str(gsm)
             times = []
             for _ in range(a.reps + 1):
                 kv.reset()
@@ -79,7 +81,7 @@ def main():
             same = bool((toks == base_tokens).all())
             best = min(times[1:])
             gbs = work["decode_bytes_per_step"] / best / 1e6
-            d = dict(l2_ahead=ahead, l2_mode=mode, fast_prologue=fast, ms_per_token=best, all_ms=times,
+            d = dict(l2_ahead=ahead, l2_mode=mode, fast_prologue=fast, gamma_smem=gsm, ms_per_token=best, all_ms=times,
                      achieved_gbs=gbs, frac_hbm_peak=gbs / hbm_peak, tokens_equal_baseline=same)
             s = json.dumps(d)
             print(s, flush=True)
