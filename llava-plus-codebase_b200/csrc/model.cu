@@ -1062,6 +1062,10 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
     cudaMemset(kv->tok.p, 0, (size_t)max_batch * 4);
     cudaMemset(kv->step_counter.p, 0, 4);
     cudaMemset(kv->attn_counters.p, 0, (size_t)max_batch * m->d.heads * 4);
+    // The memsets above run on the legacy stream; the caller's stream may be a non-blocking one (torch side streams are) and
+    // is NOT ordered against it: a prefill issued right after this call would race with the zero-fill of the cache it writes
+    // (seen in scripts/decode_ab.py FRESHKV=1: different tokens on a cache that was created a moment earlier).
+    B2_CUDA_CHECK(cudaDeviceSynchronize());
     kv->len_host.assign(max_batch, 0);
     *out = kv;
     return 0;
@@ -1075,6 +1079,13 @@ int b2_kv_reset(b2_kv* kv) {
     // decode call, both on the CALLER's stream; a cudaMemset here would run on the legacy stream, unordered against work
     // still in flight on a non-blocking caller stream (e.g. two forward() calls issued back to back).
     kv->len_host.assign(kv->max_batch, 0);
+    {   // measurement knob: drop the captured decode graph so that the next run starts with an eager step + a new capture
+        const char* e = getenv("B2_KV_RESET_GRAPH");
+        if (e != nullptr && e[0] == '1') {
+            if (kv->graph) { cudaGraphExecDestroy(kv->graph); kv->graph = nullptr; kv->graph_B = 0; }
+            kv->warm_B = 0;
+        }
+    }
     return 0;
 }
 

@@ -74,6 +74,8 @@ def full(tag, rep):
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    if len(sys.argv) > 2:   # on the GPU box: write the text summaries next to the reports (only gpurun_out/ travels back,
+        PROF = sys.argv[2]  # and it is capped at 64 MiB: the .ncu-rep files themselves are deleted by the calling script)
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
     import glob
