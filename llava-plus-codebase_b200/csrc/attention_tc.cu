@@ -95,7 +95,7 @@ struct FlashTcParams {
     int64_t o_bs, o_ts, o_hs;
     int S;
     float scale_log2;
-    int exp_poly;  // every second exp2 of the softmax on the FMA/ALU pipes instead of MUFU (B2_FLASH_EXP_POLY=0 turns it off)
+    int exp_poly;  // every second exp2 of the softmax on the FMA/ALU pipes instead of MUFU (B2_FLASH_EXP_POLY=1; measured slower)
 };
 
 template <int D>
@@ -391,8 +391,10 @@ int launch_tc(const FlashArgs& a, cudaStream_t stream) {
     p.S = a.S;
     p.scale_log2 = a.scale * 1.4426950408889634f;
     {
+        // measured on B200 (profiles/r2g_attn_bench.txt): 3 % SLOWER at every shape (ViT B=32: 220 vs 213 us) — the softmax
+        // warps are not MUFU-bound after all at two CTAs per SM; kept as a knob, off by default
         const char* e = getenv("B2_FLASH_EXP_POLY");
-        p.exp_poly = !(e != nullptr && e[0] == '0');
+        p.exp_poly = (e != nullptr && e[0] == '1');
     }
     constexpr int smem = TcCfg<D>::SMEM;
     static bool attr_set = false;
