@@ -547,6 +547,17 @@ int rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, in
     return 0;
 }
 
+// resident CTAs of decode_attn_kernel per SM (register-limited: 79 registers x 128 threads -> 6), for the split heuristic
+int decode_attn_ctas_per_sm() {
+    static int occ = 0;
+    if (occ == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_attn_kernel, DA_THREADS, 0) != cudaSuccess || n < 1) n = 6;
+        occ = n;
+    }
+    return occ;
+}
+
 int decode_attn_bf16(const DecodeAttnArgs& a, cudaStream_t stream) {
     B2_CHECK_ARG(a.D == DA_D, "decode_attn: head_dim must be 128 (got %d)", a.D);
     B2_CHECK_ARG(a.nsplit >= 1 && a.B > 0 && a.H > 0, "decode_attn: bad launch shape");

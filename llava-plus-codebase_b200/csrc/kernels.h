@@ -124,6 +124,7 @@ struct DecodeAttnArgs {
     int B = 0, H = 0, D = 128, Smax = 0, nsplit = 1;
     float theta = 10000.f, scale = 1.f;
 };
+int decode_attn_ctas_per_sm();
 int decode_attn_bf16(const DecodeAttnArgs& a, cudaStream_t stream);
 
 // ---- persistent decode-step megakernel (decode_mega.cu), batch <= 8 ------------------------------------

@@ -256,11 +256,20 @@ bool use_skinny(const b2_kv* kv, int B) {
     return !(e != nullptr && e[0] == '0');
 }
 
-int decode_nsplit(int B, int H) {
-    // measured (profiles/r1e_op_bench_b16_b32.jsonl): at B*H = 1024 pairs two splits beat one by 13% (77 vs 89 us/layer)
-    int n = (8 * num_sms() + B * H - 1) / (B * H);
-    if (n < 1) n = 1;
-    if (n > 32) n = 32;
+int decode_nsplit(int B, int H, int max_seq) {
+    // Split-KV factor of the multi-kernel decode step. The kernel is register-limited to `occ` resident CTAs per SM (6), so
+    // one wave is occ*SMs = 888 CTAs. Measured over the ladder (profiles/r2j_*, r2k_decode_ab_nsplit_stages.jsonl, 7B, ctx ~800):
+    // B=8 (256 pairs): n=3 4.19 ms vs n=5 4.32 / n=10 4.38; B=16: n=3 4.80 vs n=1 5.05 / n=5 4.90; B=32: n=3 6.50 vs n=2 6.55 /
+    // n=6 6.68; B=64: n=1..3 equal. Few pairs: fill one wave; otherwise 3 splits (short enough ranges for the tail wave to
+    // overlap, few enough partials for the merge to stay cheap).
+    const char* e = getenv("B2_DECODE_NSPLIT");
+    if (e != nullptr && atoi(e) >= 1) return atoi(e) > 32 ? 32 : atoi(e);
+    const int cap = decode_attn_ctas_per_sm() * num_sms();
+    int n = cap / (B * H);
+    if (n < 3) n = 3;
+    if (n > 16) n = 16;
+    const int n_hi = max_seq / 64;  // keep >= 64 keys per split at the cache's capacity
+    if (n > n_hi) n = n_hi < 1 ? 1 : n_hi;
     return n;
 }
 
@@ -487,7 +496,7 @@ int encode_chunk(b2_model* m, const void* pixels, int n, void* out, cudaStream_t
 int decode_step_launch(b2_model* m, b2_kv* kv, int B, cudaStream_t st) {
     const b2_model_desc& d = m->d;
     const int h = d.hidden, I = d.inter, H = d.heads, V = d.vocab;
-    const int nsplit = decode_nsplit(B, H);
+    const int nsplit = decode_nsplit(B, H, kv->max_seq);
     B2_TRY(embed_tokens(kv->tok.as<int32_t>(), m->embed.p, m->x.p, B, h, V, m->err_dev, st));
     // batch <= 8: tensor-core GEMV kernels (falls back to the skinny-M tcgen05 GEMM when the activations do not fit smem)
     // batch 7..128: swap-AB stream-K GEMM (weights streamed once, all SMs busy); otherwise GEMV kernels (B <= 8) or
