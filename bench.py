@@ -138,10 +138,49 @@ CPU_THREADS = 16  # PyTorch's CPU GEMV/GEMM get SLOWER with every hardware threa
                   # 128-thread hosts in round 1: 16 threads 13.1 tok/s, 64 threads 9.7, 128 threads 3.7): a fixed, stated count
 
 
+_CPU_PIN = {}
+
+
+def _physical_cores():
+    """One logical CPU per physical core, in id order (the first hyper-thread sibling of each core), from sysfs."""
+    allowed = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    seen, cores = set(), []
+    for c in allowed:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            cores.append(c)
+    return cores
+
+
 def cpu_threads():
+    """Fixed thread count, PINNED: the intra-op pool is sized to CPU_THREADS and the process is restricted to that many distinct
+    physical cores (lowest ids) for the duration of the CPU arm, so the figure does not depend on where the scheduler happens to
+    put 16 threads on a 128-thread host. `cpu_unpin()` restores the previous affinity."""
     n = min(CPU_THREADS, os.cpu_count() or 1)
     torch.set_num_threads(n)
+    if hasattr(os, "sched_setaffinity") and "prev" not in _CPU_PIN:
+        try:
+            prev = os.sched_getaffinity(0)
+            cores = _physical_cores()[:n]
+            if len(cores) == n:
+                os.sched_setaffinity(0, cores)
+                _CPU_PIN.update(prev=prev, cores=cores)
+        except OSError:
+            pass
     return n
+
+
+def cpu_unpin():
+    prev = _CPU_PIN.pop("prev", None)
+    if prev is not None:
+        try:
+            os.sched_setaffinity(0, prev)
+        except OSError:
+            pass
 
 
 def pick_cpu_dtype():
@@ -218,7 +257,7 @@ def cpu_reference_sample(m, S, N, sample_layers=8, decode_steps=4, dtype=None):
                 dtype="bf16" if dtype == torch.bfloat16 else "f32", extrapolated=True, sampled_layers=sample_layers,
                 full_step_s=total,
                 sample=(f"EXTRAPOLATED: oracle port ({str(dtype).replace('torch.', '')}, the faster of fp32/bf16 on this host; "
-                        f"{torch.get_num_threads()} threads fixed, host has {os.cpu_count()}) at full {m['name']} dims: ViT+projector "
+                        f"{torch.get_num_threads()} threads fixed, pinned to cores {_CPU_PIN.get('cores', 'unpinned')}, host has {os.cpu_count()}) at full {m['name']} dims: ViT+projector "
                         f"1 image in full, {sample_layers} of {L} decoder layers for an S={S} prefill (lm_head on all positions, "
                         f"as the reference does) and {decode_steps} decode steps, per-layer time extrapolated x{L}/{sample_layers}"),
                 breakdown=dict(encode_s=t_enc, prefill_s=t_prefill, decode_step_s=t_decode_step,
@@ -682,8 +721,13 @@ def run_ours(args):
     if configs is not None:
         out["configs"] = configs
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_reference_sample(m, S, N)
+        cpu_reference_sample(m, S, N, sample_layers=1, decode_steps=1)   # warm-up: thread pool, allocator, weights
+        cbs = [cpu_reference_sample(m, S, N) for _ in range(2)]
+        cpu_unpin()
+        cb = dict(cbs[-1])
+        cb["value"] = sum(c["value"] for c in cbs) / len(cbs)
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "breakdown", "extrapolated", "sampled_layers")}
+        out["cpu_baseline"]["samples_tok_s"] = [c["value"] for c in cbs]
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
