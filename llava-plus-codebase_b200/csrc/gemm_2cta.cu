@@ -48,6 +48,11 @@ struct PairEpi {
     const __nv_bfloat16* residual;
     void* out;
     int ld_out, ld_res, out_fp32;
+    // ACT_ROPE_QKV
+    const float2* rope_tab;
+    __nv_bfloat16* kcache;
+    __nv_bfloat16* vcache;
+    int rope_S, rope_H, rope_Smax;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -106,6 +111,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 __device__ __forceinline__ float p_quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float p_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float p_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// q*cos + rotate_half(q)*sin with bf16 rounding of each product and of the sum (attention.cu rope_apply: same expression)
+__device__ __forceinline__ float p_rope(float x, float partner_signed, float c, float s) {
+    return round_bf16(round_bf16(x * c) + round_bf16(partner_signed * s));
+}
 
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
@@ -248,6 +257,47 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                         }
                     }
                 }
+            } else if constexpr (ACT == ACT_ROPE_QKV) {
+                // This warp's half of the pair tile is the 128 columns of ONE head of q, k or v (hidden % 256 == 0, head_dim 128).
+                // Element i of the head rotates with element i + 64: the two 32-column chunks j and j + 2 are read together.
+                const int col_base = n_blk * P_TN + half * 128;
+                const int hdim = ep.rope_H * 128;
+                const int part = col_base / hdim;  // 0 = q, 1 = k, 2 = v
+                const int head = (col_base - part * hdim) >> 7;
+                const int b = row / ep.rope_S, tpos = row - b * ep.rope_S;
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t lo[32], hi[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr_row + half * 128 + j * 32, lo);
+                    tmem_ld_32x32(taddr_row + half * 128 + 64 + j * 32, hi);
+                    tmem_ld_wait();
+                    if (!(row_ok && col_base < N)) continue;
+                    __nv_bfloat16* dst;
+                    if (part == 0) dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ld_out + col_base + j * 32;
+                    else dst = (part == 1 ? ep.kcache : ep.vcache) + (((size_t)b * ep.rope_H + head) * ep.rope_Smax + tpos) * 128 + j * 32;
+                    const float2* tab = ep.rope_tab + (size_t)tpos * 64 + j * 32;
+#pragma unroll
+                    for (int v8 = 0; v8 < 4; ++v8) {
+                        float ol[8], oh[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float xl = round_bf16(__uint_as_float(lo[v8 * 8 + e]));  // the projection as bf16, like the unfused path
+                            const float xh = round_bf16(__uint_as_float(hi[v8 * 8 + e]));
+                            if (part < 2) {
+                                const float2 cs = __ldg(tab + v8 * 8 + e);
+                                ol[e] = p_rope(xl, -xh, cs.x, cs.y);
+                                oh[e] = p_rope(xh, xl, cs.x, cs.y);
+                            } else {
+                                ol[e] = xl; oh[e] = xh;
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(dst + v8 * 8) =
+                            make_uint4(pack_bf16(ol[0], ol[1]), pack_bf16(ol[2], ol[3]), pack_bf16(ol[4], ol[5]), pack_bf16(ol[6], ol[7]));
+                        *reinterpret_cast<uint4*>(dst + 64 + v8 * 8) =
+                            make_uint4(pack_bf16(oh[0], oh[1]), pack_bf16(oh[2], oh[3]), pack_bf16(oh[4], oh[5]), pack_bf16(oh[6], oh[7]));
+                    }
+                }
             } else {
 #pragma unroll 1
                 for (int c = half * (P_TN / 64); c < (half + 1) * (P_TN / 64); ++c) {
@@ -342,11 +392,22 @@ int gemm_bf16_2cta(const GemmArgs& g, cudaStream_t stream) {
     ep.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
     ep.residual = reinterpret_cast<const __nv_bfloat16*>(g.residual);
     ep.out = g.out; ep.ld_out = g.ld_out; ep.ld_res = g.ld_res; ep.out_fp32 = g.out_fp32;
+    ep.rope_tab = reinterpret_cast<const float2*>(g.rope.table);
+    ep.kcache = reinterpret_cast<__nv_bfloat16*>(g.rope.kcache); ep.vcache = reinterpret_cast<__nv_bfloat16*>(g.rope.vcache);
+    ep.rope_S = g.rope.S; ep.rope_H = g.rope.H; ep.rope_Smax = g.rope.Smax;
+    if (g.act == ACT_ROPE_QKV) {
+        B2_CHECK_ARG(g.rope.table && g.rope.kcache && g.rope.vcache && g.rope.S > 0 && g.rope.H > 0 && g.rope.Smax >= g.rope.S,
+                     "gemm_2cta(rope_qkv): rope arguments missing");
+        B2_CHECK_ARG(g.N == 3 * g.rope.H * 128 && (g.rope.H * 128) % 256 == 0 && g.M % g.rope.S == 0 && !g.out_fp32 &&
+                         g.bias == nullptr && g.residual == nullptr,
+                     "gemm_2cta(rope_qkv): needs N = 3*H*128 with H*128 %% 256 == 0, M = B*S, bf16 output, no bias/residual");
+    }
     switch (g.act) {
         case ACT_NONE: return launch_pair<ACT_NONE>(ta, tb, g.M, g.N, g.K, ep, stream);
         case ACT_QUICK_GELU: return launch_pair<ACT_QUICK_GELU>(ta, tb, g.M, g.N, g.K, ep, stream);
         case ACT_GELU_ERF: return launch_pair<ACT_GELU_ERF>(ta, tb, g.M, g.N, g.K, ep, stream);
         case ACT_SWIGLU: return launch_pair<ACT_SWIGLU>(ta, tb, g.M, g.N, g.K, ep, stream);
+        case ACT_ROPE_QKV: return launch_pair<ACT_ROPE_QKV>(ta, tb, g.M, g.N, g.K, ep, stream);
         default: break;
     }
     set_error("gemm_2cta: unsupported activation %d", g.act);

@@ -7,7 +7,17 @@
 
 namespace b2 {
 
-enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_SWIGLU = 3 };
+enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_SWIGLU = 3, ACT_ROPE_QKV = 4 };
+
+// ACT_ROPE_QKV (CTA-pair kernel only): the GEMM is LLaMA's fused QKV projection of a prefill, rows = b*S + t. The epilogue
+// rounds the projection to bf16, applies RoPE (HF rounding points, cos/sin from `table`) to the q and k heads, writes q to
+// `out` and k / v straight into the KV cache [b][head][Smax][128] — the standalone rope_kv_write pass over qkv disappears.
+struct RopeQkv {
+    const void* table = nullptr;   // float2 [Smax][64]: (cos, sin) of position t, frequency i, bf16-rounded (rope_table_build)
+    void* kcache = nullptr;        // this layer's K slab of the first batch row written
+    void* vcache = nullptr;
+    int S = 0, H = 0, Smax = 0;
+};
 enum { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
 
 int num_sms();
@@ -24,6 +34,7 @@ struct GemmArgs {
     int M = 0, N = 0, K = 0;
     int act = ACT_NONE;
     int bn_override = 0;  // 0 = cost-model heuristic, else 64/128/192/256 (2 = CTA-pair kernel)
+    RopeQkv rope;         // ACT_ROPE_QKV only
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 // mm_projector mlp2x_gelu as ONE kernel (gemm_tcgen05.cu, projector_fused_kernel): out = gelu_erf(X W1^T + b1) W2^T + b2.
@@ -109,6 +120,8 @@ int flash_attn_mma_bf16(const FlashArgs& a, cudaStream_t stream);  // attention.
 
 // prefill: RoPE on q (in place) and k inside qkv [B*S, 3*H*D]; roped k and v written to the cache
 // kcache/vcache: [Bmax, H, Smax, D] for one layer. Positions are 0..S-1 (right-padded rows).
+// (cos, sin) table of rope_kv_write's positions 0..Smax-1 (head_dim D): float2 [Smax][D/2]
+int rope_table_build(void* table, int Smax, int D, float theta, cudaStream_t stream);
 int rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, int D, int Smax, float theta,
                   cudaStream_t stream);
 

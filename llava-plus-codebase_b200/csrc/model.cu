@@ -130,6 +130,7 @@ struct b2_kv {
     // run on this library-owned stream, ordered against the caller's stream with events
     unsigned int mega_bar_base = 0;  // value of the grid-barrier counter before the next megakernel launch
     DevBuf mega_layers, mega_sync;  // MegaLayer[L] table and {bar_count, bar_gen, done_count}
+    DevBuf rope_tab;                // float2 [max_seq][hd/2]: (cos, sin) per position for the QKV GEMM's fused RoPE epilogue
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int warm_B = 0;  // an eager step has run for this B (function attributes set, driver entry points resolved)
@@ -1071,6 +1072,11 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
     cudaMemset(kv->tok.p, 0, (size_t)max_batch * 4);
     cudaMemset(kv->step_counter.p, 0, 4);
     cudaMemset(kv->attn_counters.p, 0, (size_t)max_batch * m->d.heads * 4);
+    if ((r = kv->rope_tab.alloc((size_t)max_seq * (m->hd / 2) * sizeof(float2))) != 0 ||
+        (r = rope_table_build(kv->rope_tab.p, max_seq, m->hd, m->d.rope_theta, nullptr)) != 0) {
+        b2_kv_destroy(kv);
+        return r;
+    }
     // The memsets above run on the legacy stream; the caller's stream may be a non-blocking one (torch side streams are) and
     // is NOT ordered against it: a prefill issued right after this call would race with the zero-fill of the cache it writes
     // (seen in scripts/decode_ab.py FRESHKV=1: different tokens on a cache that was created a moment earlier).
@@ -1108,7 +1114,7 @@ int b2_kv_destroy(b2_kv* kv) {
     if (kv->ev_fork) cudaEventDestroy(kv->ev_fork);
     if (kv->ev_join) cudaEventDestroy(kv->ev_join);
     DevBuf* bs[] = {&kv->k, &kv->v, &kv->len_dev, &kv->tok, &kv->step_counter, &kv->out_tokens, &kv->attn_partial,
-                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters, &kv->sstate, &kv->rows_dev};
+                    &kv->attn_counters, &kv->mega_layers, &kv->mega_sync, &kv->sk_partial, &kv->sk_counters, &kv->sstate, &kv->rows_dev, &kv->rope_tab};
     for (DevBuf* b : bs) b->free();
     delete kv;
     return 0;
@@ -1243,13 +1249,26 @@ int b2_prefill_slots(b2_model* m, b2_kv* kv, const void* embeds, const int32_t* 
     const size_t slot_off = (size_t)slot0 * H * kv->max_seq * m->hd;  // cache slabs of the first slot this call fills
 
     B2_CUDA_CHECK(cudaMemcpyAsync(m->x.p, embeds, (size_t)T * h * 2, cudaMemcpyDeviceToDevice, st));
+    // RoPE + KV write fused into the QKV GEMM where the CTA-pair kernel is the one that runs anyway (M >= 512; 256-column pair
+    // tiles must hold whole 128-wide heads of ONE of q / k / v: hidden % 256 == 0). B2_ROPE_FUSED=0: standalone pass (A/B, tests).
+    bool rope_fused = T >= 512 && m->hd == 128 && h % 256 == 0;
+    { const char* e = getenv("B2_ROPE_FUSED"); if (e != nullptr && e[0] == '0') rope_fused = false; }
     for (int l = 0; l < d.layers; ++l) {
         LlamaLayer& L = m->ll[l];
         bf16* kc = kv->k.as<bf16>() + (size_t)l * kv->layer_stride() + slot_off;
         bf16* vc = kv->v.as<bf16>() + (size_t)l * kv->layer_stride() + slot_off;
         B2_TRY(rmsnorm_bf16(m->x.p, h, L.ln1.p, m->xn.p, T, h, d.rms_eps, st));
-        B2_TRY(gemm(m->xn.p, h, L.wqkv.p, h, nullptr, nullptr, 0, m->qkv.p, 3 * h, 0, T, 3 * h, h, ACT_NONE, st));
-        B2_TRY(rope_kv_write(m->qkv.p, kc, vc, B, S, H, m->hd, kv->max_seq, d.rope_theta, st));
+        if (rope_fused) {
+            // QKV projection with RoPE and the cache write in its epilogue (CTA-pair kernel): q -> qkv buffer, k / v -> cache
+            GemmArgs g;
+            g.A = m->xn.p; g.lda = h; g.W = L.wqkv.p; g.ldw = h; g.out = m->qkv.p; g.ld_out = 3 * h;
+            g.M = T; g.N = 3 * h; g.K = h; g.act = ACT_ROPE_QKV;
+            g.rope.table = kv->rope_tab.p; g.rope.kcache = kc; g.rope.vcache = vc; g.rope.S = S; g.rope.H = H; g.rope.Smax = kv->max_seq;
+            B2_TRY(gemm_bf16_2cta(g, st));
+        } else {
+            B2_TRY(gemm(m->xn.p, h, L.wqkv.p, h, nullptr, nullptr, 0, m->qkv.p, 3 * h, 0, T, 3 * h, h, ACT_NONE, st));
+            B2_TRY(rope_kv_write(m->qkv.p, kc, vc, B, S, H, m->hd, kv->max_seq, d.rope_theta, st));
+        }
         FlashArgs fa;
         fa.q = m->qkv.p; fa.q_bs = (int64_t)S * 3 * h; fa.q_ts = 3 * h; fa.q_hs = m->hd;
         fa.k = kc; fa.k_bs = (int64_t)H * kv->max_seq * m->hd; fa.k_ts = m->hd; fa.k_hs = (int64_t)kv->max_seq * m->hd;
