@@ -61,7 +61,9 @@ class RequestStream:
 
 
 class ContinuousBatcher:
-    def __init__(self, engine, slots, max_seq):
+    def __init__(self, engine, slots, max_seq, _cuda=None):
+        """`_cuda`: the namespace streams / events come from (torch.cuda; the CPU tests of the scheduling logic pass a stand-in)."""
+        self._cuda = _cuda if _cuda is not None else torch.cuda
         if slots < 2:
             raise ValueError("continuous batching needs at least 2 slots")
         self.engine, self.slots, self.max_seq = engine, int(slots), int(max_seq)
@@ -73,8 +75,8 @@ class ContinuousBatcher:
         self.wake = threading.Event()
         self.closed = False
         self.stats = {"steps": 0, "admitted": 0, "max_active": 0, "rows_stepped": 0}
-        self.stream = torch.cuda.Stream(device=engine.device)
-        with torch.cuda.stream(self.stream):
+        self.stream = self._cuda.Stream(device=engine.device)
+        with self._cuda.stream(self.stream):
             engine.batch_begin(self.kv, self.slots)
         self.thread = threading.Thread(target=self._loop, name="b2-batcher", daemon=True)
         self.thread.start()
@@ -86,7 +88,7 @@ class ContinuousBatcher:
             raise RuntimeError("batcher is closed")
         if length + max_new_tokens > self.max_seq:
             raise ValueError(f"sequence {length} + {max_new_tokens} new tokens exceeds the batcher's cache ({self.max_seq})")
-        ready = torch.cuda.Event()
+        ready = self._cuda.Event()
         ready.record()                          # the caller's stream produced `embeds`: the scheduler's stream waits for it
         req = Request(embeds, length, sampling or make_sampling(), max_new_tokens)
         req.ready = ready
@@ -129,7 +131,7 @@ class ContinuousBatcher:
     def _loop(self):
         eng = self.engine
         try:
-            with torch.cuda.stream(self.stream), torch.no_grad():
+            with self._cuda.stream(self.stream), torch.no_grad():
                 while not self.closed:
                     for slot in [s for s, r in self.active.items() if r.cancelled]:
                         self._retire(slot)
