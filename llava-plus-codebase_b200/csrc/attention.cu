@@ -257,14 +257,15 @@ __device__ __forceinline__ float rope_apply(float x, float partner_signed, float
     return round_bf16(round_bf16(x * c) + round_bf16(partner_signed * s));
 }
 
-// the same (cos, sin) values as a table [Smax][D/2] for the QKV GEMM's fused RoPE epilogue (gemm_2cta.cu, ACT_ROPE_QKV)
-__global__ void rope_table_kernel(float2* __restrict__ table, int Smax, int D, float theta) {
+// the same (cos, sin) values as a table [Smax][D/2] of bf16 pairs (cos | sin << 16) for the QKV GEMM's fused RoPE epilogue
+// (gemm_2cta.cu, ACT_ROPE_QKV)
+__global__ void rope_table_kernel(uint32_t* __restrict__ table, int Smax, int D, float theta) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = D / 2;
     if (idx >= Smax * half) return;
     float c, s;
     rope_cos_sin(idx / half, idx % half, D, theta, c, s);
-    table[idx] = make_float2(c, s);
+    table[idx] = pack_bf16(c, s);  // both are bf16-rounded already: the packing is exact
 }
 
 // grid: (B*S) tokens, 256 threads. The D/2 (cos, sin) pairs of the token's position are tabulated once in shared
@@ -548,7 +549,7 @@ int flash_attn_mma_bf16(const FlashArgs& a, cudaStream_t stream) {
 int rope_table_build(void* table, int Smax, int D, float theta, cudaStream_t stream) {
     B2_CHECK_ARG(table != nullptr && Smax > 0 && D > 0 && D % 2 == 0, "rope_table_build: bad argument");
     const int n = Smax * (D / 2);
-    rope_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(table), Smax, D, theta);
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(table), Smax, D, theta);
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -49,7 +49,7 @@ struct PairEpi {
     void* out;
     int ld_out, ld_res, out_fp32;
     // ACT_ROPE_QKV
-    const float2* rope_tab;
+    const uint32_t* rope_tab;
     __nv_bfloat16* kcache;
     __nv_bfloat16* vcache;
     int rope_S, rope_H, rope_Smax;
@@ -276,18 +276,24 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     __nv_bfloat16* dst;
                     if (part == 0) dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ld_out + col_base + j * 32;
                     else dst = (part == 1 ? ep.kcache : ep.vcache) + (((size_t)b * ep.rope_H + head) * ep.rope_Smax + tpos) * 128 + j * 32;
-                    const float2* tab = ep.rope_tab + (size_t)tpos * 64 + j * 32;
+                    const uint4* tab = reinterpret_cast<const uint4*>(ep.rope_tab + (size_t)tpos * 64 + j * 32);  // 8 x 16 B: 32 (cos, sin) pairs
 #pragma unroll
                     for (int v8 = 0; v8 < 4; ++v8) {
                         float ol[8], oh[8];
+                        uint32_t csw[8];
+                        if (part < 2) {
+                            const uint4 t0 = __ldg(tab + v8 * 2), t1 = __ldg(tab + v8 * 2 + 1);
+                            csw[0] = t0.x; csw[1] = t0.y; csw[2] = t0.z; csw[3] = t0.w;
+                            csw[4] = t1.x; csw[5] = t1.y; csw[6] = t1.z; csw[7] = t1.w;
+                        }
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const float xl = round_bf16(__uint_as_float(lo[v8 * 8 + e]));  // the projection as bf16, like the unfused path
                             const float xh = round_bf16(__uint_as_float(hi[v8 * 8 + e]));
                             if (part < 2) {
-                                const float2 cs = __ldg(tab + v8 * 8 + e);
-                                ol[e] = p_rope(xl, -xh, cs.x, cs.y);
-                                oh[e] = p_rope(xh, xl, cs.x, cs.y);
+                                const float cs_c = bf16_lo(csw[e]), cs_s = bf16_hi(csw[e]);
+                                ol[e] = p_rope(xl, -xh, cs_c, cs_s);
+                                oh[e] = p_rope(xh, xl, cs_c, cs_s);
                             } else {
                                 ol[e] = xl; oh[e] = xh;
                             }
@@ -392,7 +398,7 @@ int gemm_bf16_2cta(const GemmArgs& g, cudaStream_t stream) {
     ep.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
     ep.residual = reinterpret_cast<const __nv_bfloat16*>(g.residual);
     ep.out = g.out; ep.ld_out = g.ld_out; ep.ld_res = g.ld_res; ep.out_fp32 = g.out_fp32;
-    ep.rope_tab = reinterpret_cast<const float2*>(g.rope.table);
+    ep.rope_tab = reinterpret_cast<const uint32_t*>(g.rope.table);
     ep.kcache = reinterpret_cast<__nv_bfloat16*>(g.rope.kcache); ep.vcache = reinterpret_cast<__nv_bfloat16*>(g.rope.vcache);
     ep.rope_S = g.rope.S; ep.rope_H = g.rope.H; ep.rope_Smax = g.rope.Smax;
     if (g.act == ACT_ROPE_QKV) {

@@ -13,7 +13,7 @@ enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_SWIGLU = 3, ACT_R
 // rounds the projection to bf16, applies RoPE (HF rounding points, cos/sin from `table`) to the q and k heads, writes q to
 // `out` and k / v straight into the KV cache [b][head][Smax][128] — the standalone rope_kv_write pass over qkv disappears.
 struct RopeQkv {
-    const void* table = nullptr;   // float2 [Smax][64]: (cos, sin) of position t, frequency i, bf16-rounded (rope_table_build)
+    const void* table = nullptr;   // uint32 [Smax][64]: bf16 cos | bf16 sin << 16 of position t, frequency i (rope_table_build)
     void* kcache = nullptr;        // this layer's K slab of the first batch row written
     void* vcache = nullptr;
     int S = 0, H = 0, Smax = 0;
@@ -120,7 +120,7 @@ int flash_attn_mma_bf16(const FlashArgs& a, cudaStream_t stream);  // attention.
 
 // prefill: RoPE on q (in place) and k inside qkv [B*S, 3*H*D]; roped k and v written to the cache
 // kcache/vcache: [Bmax, H, Smax, D] for one layer. Positions are 0..S-1 (right-padded rows).
-// (cos, sin) table of rope_kv_write's positions 0..Smax-1 (head_dim D): float2 [Smax][D/2]
+// (cos, sin) table of rope_kv_write's positions 0..Smax-1 (head_dim D): uint32 [Smax][D/2], bf16 cos | bf16 sin << 16
 int rope_table_build(void* table, int Smax, int D, float theta, cudaStream_t stream);
 int rope_kv_write(void* qkv, void* kcache, void* vcache, int B, int S, int H, int D, int Smax, float theta,
                   cudaStream_t stream);

@@ -130,7 +130,7 @@ struct b2_kv {
     // run on this library-owned stream, ordered against the caller's stream with events
     unsigned int mega_bar_base = 0;  // value of the grid-barrier counter before the next megakernel launch
     DevBuf mega_layers, mega_sync;  // MegaLayer[L] table and {bar_count, bar_gen, done_count}
-    DevBuf rope_tab;                // float2 [max_seq][hd/2]: (cos, sin) per position for the QKV GEMM's fused RoPE epilogue
+    DevBuf rope_tab;                // uint32 [max_seq][hd/2]: bf16 (cos, sin) per position for the QKV GEMM's fused RoPE epilogue
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int warm_B = 0;  // an eager step has run for this B (function attributes set, driver entry points resolved)
@@ -1072,7 +1072,7 @@ int b2_kv_create(b2_model* m, int max_batch, int max_seq, b2_kv** out) {
     cudaMemset(kv->tok.p, 0, (size_t)max_batch * 4);
     cudaMemset(kv->step_counter.p, 0, 4);
     cudaMemset(kv->attn_counters.p, 0, (size_t)max_batch * m->d.heads * 4);
-    if ((r = kv->rope_tab.alloc((size_t)max_seq * (m->hd / 2) * sizeof(float2))) != 0 ||
+    if ((r = kv->rope_tab.alloc((size_t)max_seq * (m->hd / 2) * sizeof(uint32_t))) != 0 ||
         (r = rope_table_build(kv->rope_tab.p, max_seq, m->hd, m->d.rope_theta, nullptr)) != 0) {
         b2_kv_destroy(kv);
         return r;
