@@ -119,3 +119,45 @@ def test_streamer_and_stopping_criteria_protocol():
 def test_tensor_valued_criteria_are_accepted():
     out, _ = run([4, 9], 20, set(), 0, 4, criteria=[lambda ids, s: torch.tensor([ids.shape[1] >= 6, True])])
     assert out.shape[1] == 3  # prompt_len 3 + 3 new tokens = 6 columns
+
+
+def test_kv_pool_hands_out_exclusive_caches_and_blocks_at_its_cap():
+    """_KVPool (one cache per generate() call): caches are created on demand up to `cap`, reused after release, and a
+    third concurrent acquire waits for a release instead of sharing a cache (per-generate KV cache)."""
+    import threading
+    import time
+    from llava.model.language_model.llava_llama import _KVPool
+
+    class Eng:
+        made = 0
+
+        def new_kv(self, max_batch, max_seq):
+            Eng.made += 1
+            return object()
+
+    pool = _KVPool(Eng(), max_batch=2, max_seq=64, cap=2)
+    a, b = pool.acquire(), pool.acquire()
+    assert a is not b and Eng.made == 2
+    got = []
+    t = threading.Thread(target=lambda: got.append(pool.acquire()))
+    t.start()
+    time.sleep(0.1)
+    assert not got                     # cap reached: the third caller waits
+    pool.release(a)
+    t.join(timeout=5)
+    assert got == [a] and Eng.made == 2  # ... and gets the released cache, not a new one
+    pool.release(b)
+    assert pool.acquire() is b
+
+    class Failing:
+        def new_kv(self, max_batch, max_seq):
+            raise MemoryError("no room for another cache")
+
+    bad = _KVPool(Failing(), 1, 8, cap=1)
+    for _ in range(2):                 # a failed creation gives its place back (the second attempt must not dead-lock)
+        try:
+            bad.acquire()
+        except MemoryError:
+            pass
+        else:
+            raise AssertionError("expected MemoryError")
